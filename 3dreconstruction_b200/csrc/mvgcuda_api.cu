@@ -1,0 +1,714 @@
+// mvgcuda_api.cu -- C ABI of libmvgcuda (include/mvgcuda.h): context, HBM arena, batch pipeline.
+//
+// Host-side structure (B200-first, not a translation of the reference's per-pair loop,
+// matcher_all_in_memory.h:71-139): all descriptor arrays are resident in one HBM arena, the pair
+// list is cut into batches, each batch is ONE persistent launch of the fused kernel over
+// (pair, 128-query block) work items followed by three small compaction launches, and only the
+// compacted matches travel back over PCIe.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mvgcuda.h"
+#include "kernels.cuh"
+
+namespace mvgcuda {
+
+static thread_local std::string g_create_error;
+
+#define CU_CHECK(ctx, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      (ctx)->set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MVGCUDA_ERR_CUDA;                                                                      \
+    }                                                                                               \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  // grow, preserving the first `keep` elements
+  cudaError_t reserve(size_t n, size_t keep = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = std::max(n, cap + cap / 2);
+    T* np = nullptr;
+    cudaError_t e = cudaMallocHost(&np, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep) memcpy(np, p, keep * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Arena {
+  DevBuf<uint8_t> desc;   // [rows_padded][128]
+  DevBuf<int> ccol;       // K1 output
+  DevBuf<int> img_row0, img_rows;
+  std::vector<int> row0, rows;  // host copies
+  int arena_rows = 0;
+  CUtensorMap tmap_q, tmap_db;
+  void release() { desc.release(); ccol.release(); img_row0.release(); img_rows.release(); row0.clear(); rows.clear(); arena_rows = 0; }
+};
+
+}  // namespace mvgcuda
+
+using namespace mvgcuda;
+
+struct mvgcuda_ctx {
+  int device = 0;
+  cudaDeviceProp prop{};
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  size_t knn_smem = 0;
+
+  Arena images;   // uploaded collection
+  Arena scratch;  // knn2_arrays operands
+
+  // batch buffers
+  DevBuf<PairJob> d_jobs;
+  DevBuf<int> d_item_start;
+  DevBuf<KnnRecord> d_knn;
+  DevBuf<int2> d_tmp;
+  DevBuf<int> d_npass, d_counts;
+  DevBuf<long long> d_offsets;  // [batch_pairs + 1]
+  DevBuf<long long> d_total;
+  DevBuf<int2> d_matches;
+  PinnedBuf<PairJob> h_jobs;
+  PinnedBuf<int> h_item_start;
+  PinnedBuf<long long> h_total;
+
+  // results of the last match call
+  PinnedBuf<int> r_counts;
+  PinnedBuf<long long> r_offsets;
+  PinnedBuf<int> r_matches;  // 2 ints per match
+  int64_t r_pairs = 0;
+  // results after host de-duplication (match_collection)
+  std::vector<int> c_counts;
+  std::vector<long long> c_offsets;
+  std::vector<int> c_matches;
+  bool last_was_collection = false;
+
+  std::vector<std::vector<float>> feats;  // per image [rows][2]
+
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    error = buf;
+  }
+};
+
+namespace mvgcuda {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D u8 tensor [rows][128], box {128 bytes, box_rows}, 128-byte swizzle (one row == one swizzle atom).
+static int make_tmap(mvgcuda_ctx* ctx, CUtensorMap* tm, const uint8_t* base, int rows, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { ctx->set_error("cuTensorMapEncodeTiled entry point not found"); return MVGCUDA_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kDim};
+  cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return MVGCUDA_ERR_CUDA; }
+  return MVGCUDA_OK;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Lay the images out in the arena (each starting at a multiple of kRowAlign rows, zero padded),
+// copy them in, run K1, build the tensor maps.
+static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* const* desc, const int32_t* rows,
+                      int pinned) {
+  A.row0.assign(n_images + 1, 0);
+  A.rows.assign(n_images, 0);
+  long long total = 0;
+  for (int i = 0; i < n_images; ++i) {
+    if (rows[i] < 0 || (rows[i] > 0 && !desc[i])) { ctx->set_error("image %d: bad rows/pointer", i); return MVGCUDA_ERR_INVALID; }
+    A.row0[i] = (int)total;
+    A.rows[i] = rows[i];
+    total += round_up(rows[i], kRowAlign);
+    if (total > 0x7FFF0000ll) { ctx->set_error("arena exceeds 2^31 rows"); return MVGCUDA_ERR_INVALID; }
+  }
+  A.row0[n_images] = (int)total;
+  A.arena_rows = (int)std::max<long long>(total, kRowAlign);
+  CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
+  CU_CHECK(ctx, A.ccol.reserve(A.arena_rows));
+  CU_CHECK(ctx, A.img_row0.reserve(n_images + 1));
+  CU_CHECK(ctx, A.img_rows.reserve(std::max(n_images, 1)));
+  cudaStream_t st = ctx->stream;
+  CU_CHECK(ctx, cudaMemsetAsync(A.desc.p, 0, (size_t)A.arena_rows * kDim, st));
+  for (int i = 0; i < n_images; ++i) {
+    if (rows[i] == 0) continue;
+    CU_CHECK(ctx, cudaMemcpyAsync(A.desc.p + (size_t)A.row0[i] * kDim, desc[i], (size_t)rows[i] * kDim,
+                                  cudaMemcpyHostToDevice, st));
+  }
+  (void)pinned;
+  CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_images)
+    CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long threads = (long long)A.arena_rows * 8;
+  row_consts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A.desc.p, A.img_row0.p, A.img_rows.p, n_images,
+                                                                      A.arena_rows, A.ccol.p);
+  CU_CHECK(ctx, cudaGetLastError());
+  int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
+  if (rc) return rc;
+  CU_CHECK(ctx, cudaStreamSynchronize(st));  // row0/rows vectors and caller buffers are free again
+  return MVGCUDA_OK;
+}
+
+struct BatchPlan {
+  int n_jobs = 0;
+  int n_items = 0;
+  long long n_records = 0;
+};
+
+// Fill h_jobs / h_item_start for pairs [p0, p1) of the list; images from arena A.
+static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, int64_t p0, int64_t p1, BatchPlan& bp) {
+  bp.n_jobs = (int)(p1 - p0);
+  long long rec = 0;
+  int items = 0;
+  for (int64_t p = p0; p < p1; ++p) {
+    const int I = pairs[2 * p], J = pairs[2 * p + 1];
+    PairJob& j = ctx->h_jobs.p[p - p0];
+    j.db_row0 = A.row0[I];
+    j.db_rows = A.rows[I];
+    j.q_row0 = A.row0[J];
+    j.q_rows = A.rows[J];
+    j.out_off = (int)rec;
+    j.valid = (j.db_rows >= 2 && j.q_rows >= 1) ? 1 : 0;
+    ctx->h_item_start.p[p - p0] = items;
+    if (j.valid) items += (j.q_rows + kBlockQ - 1) / kBlockQ;
+    rec += j.q_rows;
+  }
+  ctx->h_item_start.p[p1 - p0] = items;
+  bp.n_items = items;
+  bp.n_records = rec;
+}
+
+static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp) {
+  if (bp.n_items == 0) return MVGCUDA_OK;
+  KnnParams kp;
+  kp.ccol = A.ccol.p;
+  kp.jobs = ctx->d_jobs.p;
+  kp.item_start = ctx->d_item_start.p;
+  kp.n_jobs = bp.n_jobs;
+  kp.n_items = bp.n_items;
+  kp.out = ctx->d_knn.p;
+  const int grid = std::min(bp.n_items, ctx->prop.multiProcessorCount);
+  knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(A.tmap_q, A.tmap_db, kp);
+  CU_CHECK(ctx, cudaGetLastError());
+  return MVGCUDA_OK;
+}
+
+constexpr long long kBatchRecords = 24ll << 20;  // queries per batch (384 MB of KnnRecord)
+constexpr int kBatchPairs = 1 << 16;
+
+static int reserve_batch(mvgcuda_ctx* ctx, int n_jobs, long long n_records) {
+  CU_CHECK(ctx, ctx->d_jobs.reserve(n_jobs));
+  CU_CHECK(ctx, ctx->d_item_start.reserve(n_jobs + 1));
+  CU_CHECK(ctx, ctx->d_npass.reserve(n_jobs));
+  CU_CHECK(ctx, ctx->d_counts.reserve(n_jobs));
+  CU_CHECK(ctx, ctx->d_offsets.reserve(n_jobs + 1));
+  CU_CHECK(ctx, ctx->d_total.reserve(1));
+  CU_CHECK(ctx, ctx->d_knn.reserve(std::max<long long>(n_records, 1)));
+  CU_CHECK(ctx, ctx->d_tmp.reserve(std::max<long long>(n_records, 1)));
+  CU_CHECK(ctx, ctx->d_matches.reserve(std::max<long long>(n_records, 1)));
+  return MVGCUDA_OK;
+}
+
+static int validate_pairs(mvgcuda_ctx* ctx, const Arena& A, int64_t n_pairs, const int32_t* pairs) {
+  if (n_pairs < 0 || (n_pairs > 0 && !pairs)) { ctx->set_error("bad pair list"); return MVGCUDA_ERR_INVALID; }
+  const int n = (int)A.rows.size();
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const int I = pairs[2 * p], J = pairs[2 * p + 1];
+    if (I < 0 || I >= n || J < 0 || J >= n) { ctx->set_error("pair %lld: image id out of range", (long long)p); return MVGCUDA_ERR_INVALID; }
+  }
+  return MVGCUDA_OK;
+}
+
+static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,
+                            mvgcuda_pair_matches* out) {
+  const Arena& A = ctx->images;
+  int rc = validate_pairs(ctx, A, n_pairs, pairs);
+  if (rc) return rc;
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  CU_CHECK(ctx, ctx->r_counts.reserve(std::max<int64_t>(n_pairs, 1)));
+  CU_CHECK(ctx, ctx->r_offsets.reserve(n_pairs + 1));
+  CU_CHECK(ctx, ctx->h_total.reserve(1));
+  ctx->r_pairs = n_pairs;
+  ctx->last_was_collection = false;
+  float gpu_ms = 0.f, knn_ms = 0.f;
+  int knn_launches = 0, launches = 0;
+  long long match_base = 0;
+  cudaStream_t st = ctx->stream;
+
+  int64_t p0 = 0;
+  while (p0 < n_pairs) {
+    // batch = as many consecutive pairs as fit the record budget
+    int64_t p1 = p0;
+    long long rec = 0;
+    while (p1 < n_pairs && (p1 - p0) < kBatchPairs) {
+      const long long qr = A.rows[pairs[2 * p1 + 1]];
+      if (p1 > p0 && rec + qr > kBatchRecords) break;
+      rec += qr;
+      ++p1;
+    }
+    const int nb = (int)(p1 - p0);
+    CU_CHECK(ctx, ctx->h_jobs.reserve(nb));
+    CU_CHECK(ctx, ctx->h_item_start.reserve(nb + 1));
+    BatchPlan bp;
+    plan_batch(ctx, A, pairs, p0, p1, bp);
+    rc = reserve_batch(ctx, nb, bp.n_records);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jobs.p, ctx->h_jobs.p, nb * sizeof(PairJob), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_item_start.p, ctx->h_item_start.p, (nb + 1) * sizeof(int),
+                                  cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], st));
+    rc = launch_knn(ctx, A, bp);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));
+    ratio_filter_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_jobs.p, ctx->d_knn.p, ratio_sq, ctx->d_tmp.p,
+                                                        ctx->d_npass.p, ctx->d_counts.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_counts.p, nb, match_base, ctx->d_offsets.p, ctx->d_total.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    dedup_scatter_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_jobs.p, ctx->d_tmp.p, ctx->d_npass.p, ctx->d_offsets.p,
+                                                         match_base, ctx->d_matches.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[2], st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_total.p, ctx->d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->r_counts.p + p0, ctx->d_counts.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->r_offsets.p + p0, ctx->d_offsets.p, (nb + 1) * sizeof(long long),
+                                  cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaStreamSynchronize(st));
+    const long long new_total = ctx->h_total.p[0];
+    const long long nm = new_total - match_base;
+    CU_CHECK(ctx, ctx->r_matches.reserve((size_t)std::max<long long>(new_total, 1) * 2, (size_t)match_base * 2));
+    if (nm > 0) {
+      CU_CHECK(ctx, cudaMemcpyAsync(ctx->r_matches.p + match_base * 2, ctx->d_matches.p, nm * sizeof(int2),
+                                    cudaMemcpyDeviceToHost, st));
+      CU_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    float ms = 0.f;
+    CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]));
+    gpu_ms += ms;
+    if (bp.n_items) {
+      CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+      knn_ms += ms;
+      ++knn_launches;
+      ++launches;
+    }
+    launches += 3;
+    match_base = new_total;
+    p0 = p1;
+  }
+  ctx->r_offsets.p[n_pairs] = match_base;
+  if (out) {
+    out->n_pairs = n_pairs;
+    out->counts = ctx->r_counts.p;
+    out->offsets = reinterpret_cast<const int64_t*>(ctx->r_offsets.p);
+    out->matches = ctx->r_matches.p;
+    out->gpu_ms = gpu_ms;
+    out->knn_kernel_ms = knn_ms;
+    out->knn_kernel_launches = knn_launches;
+    out->total_launches = launches;
+  }
+  return MVGCUDA_OK;
+}
+
+// One pair of arena A -> KnnRecords on the host.
+static int knn2_impl(mvgcuda_ctx* ctx, const Arena& A, int db_img, int q_img, int tie_mode, int32_t* idx, float* dist) {
+  if (!idx || !dist) { ctx->set_error("null output"); return MVGCUDA_ERR_INVALID; }
+  if (tie_mode != MVGCUDA_TIE_LOWEST_INDEX && tie_mode != MVGCUDA_TIE_REFERENCE) { ctx->set_error("bad tie_mode"); return MVGCUDA_ERR_INVALID; }
+  const int n = (int)A.rows.size();
+  if (db_img < 0 || db_img >= n || q_img < 0 || q_img >= n) { ctx->set_error("image id out of range"); return MVGCUDA_ERR_INVALID; }
+  const int nI = A.rows[db_img], nq = A.rows[q_img];
+  if (nI < 2 || nq < 1) {
+    // matcher_brute_force.h:107-110
+    ctx->set_error("Too much asked nearest neighbors");
+    return MVGCUDA_ERR_INVALID;
+  }
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  CU_CHECK(ctx, ctx->h_jobs.reserve(1));
+  CU_CHECK(ctx, ctx->h_item_start.reserve(2));
+  const int32_t pr[2] = {db_img, q_img};
+  BatchPlan bp;
+  plan_batch(ctx, A, pr, 0, 1, bp);
+  int rc = reserve_batch(ctx, 1, bp.n_records);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jobs.p, ctx->h_jobs.p, sizeof(PairJob), cudaMemcpyHostToDevice, st));
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_item_start.p, ctx->h_item_start.p, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = launch_knn(ctx, A, bp);
+  if (rc) return rc;
+  if (tie_mode == MVGCUDA_TIE_REFERENCE) {
+    const int warps_per_block = 8;
+    tie_fixup_kernel<<<(nq + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        A.desc.p, ctx->h_jobs.p[0], ctx->d_knn.p);
+    CU_CHECK(ctx, cudaGetLastError());
+  }
+  std::vector<KnnRecord> rec(nq);
+  CU_CHECK(ctx, cudaMemcpyAsync(rec.data(), ctx->d_knn.p, nq * sizeof(KnnRecord), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(ctx, cudaStreamSynchronize(st));
+  for (int q = 0; q < nq; ++q) {
+    idx[2 * q] = rec[q].idx1;
+    idx[2 * q + 1] = rec[q].idx2;
+    dist[2 * q] = (float)rec[q].d1;  // exact: < 2^24
+    dist[2 * q + 1] = (float)rec[q].d2;
+  }
+  return MVGCUDA_OK;
+}
+
+// ---- host side of the collection level: IndexedMatchDecorator<float>::getDeduplicated -----------------
+// Same ordering predicate as indexed_match_decorator.h:33-53 and the same container (libstdc++
+// std::set built with the iterator-range constructor, :93-95): the predicate is not a strict weak
+// order, so the result is defined by the red-black tree's insertion behaviour and must not be
+// "simplified".
+struct DecoratedMatch {
+  float x1, y1, x2, y2;
+  int i, j;
+};
+static inline bool decorated_equal(const DecoratedMatch& a, const DecoratedMatch& b) {
+  return a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2;
+}
+struct DecoratedLess {
+  bool operator()(const DecoratedMatch& a, const DecoratedMatch& b) const {
+    if (decorated_equal(a, b)) return false;
+    if (a.x1 < b.x1) return a.y1 < b.y1;
+    if (a.x1 > b.x1) return a.y1 < b.y1;
+    return a.x1 < b.x1;  // equal x1 (or unordered): false
+  }
+};
+
+static void dedup_xy(const float* fI, const float* fJ, const int* m, int n, std::vector<int>& out) {
+  std::vector<DecoratedMatch> v(n);
+  for (int k = 0; k < n; ++k) {
+    const int I = m[2 * k], J = m[2 * k + 1];
+    v[k] = DecoratedMatch{fI[2 * I], fI[2 * I + 1], fJ[2 * J], fJ[2 * J + 1], I, J};
+  }
+  std::set<DecoratedMatch, DecoratedLess> s(v.begin(), v.end());
+  out.clear();
+  out.reserve(2 * s.size());
+  for (const DecoratedMatch& d : s) { out.push_back(d.i); out.push_back(d.j); }
+}
+
+}  // namespace mvgcuda
+
+// ================================================================================ C ABI
+extern "C" {
+
+int mvgcuda_version(void) { return 100; }
+
+int mvgcuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+const char* mvgcuda_last_error(const mvgcuda_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int mvgcuda_create(int device, mvgcuda_ctx** out) {
+  if (!out) { g_create_error = "null out pointer"; return MVGCUDA_ERR_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                     " (libmvgcuda has no CPU fallback)";
+    return MVGCUDA_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device index out of range"; return MVGCUDA_ERR_INVALID; }
+  mvgcuda_ctx* ctx = new (std::nothrow) mvgcuda_ctx();
+  if (!ctx) { g_create_error = "out of host memory"; return MVGCUDA_ERR_NOMEM; }
+  ctx->device = device;
+  auto fail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return MVGCUDA_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  if (ctx->prop.major != 10) {
+    g_create_error = std::string("device '") + ctx->prop.name + "' is sm_" + std::to_string(ctx->prop.major) +
+                     std::to_string(ctx->prop.minor) + "; libmvgcuda is built for sm_100a only";
+    delete ctx;
+    return MVGCUDA_ERR_CUDA;
+  }
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+  ctx->knn_smem = sizeof(KnnSmem) + 1024;
+  if ((e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(knn2_kernel)", e);
+  if ((e = cudaFuncSetAttribute(i8_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kBytesA + kBytesB + 1024))) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(probe)", e);
+  *out = ctx;
+  return MVGCUDA_OK;
+}
+
+void mvgcuda_destroy(mvgcuda_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->images.release();
+  ctx->scratch.release();
+  ctx->d_jobs.release(); ctx->d_item_start.release(); ctx->d_knn.release(); ctx->d_tmp.release();
+  ctx->d_npass.release(); ctx->d_counts.release(); ctx->d_offsets.release(); ctx->d_total.release();
+  ctx->d_matches.release();
+  ctx->h_jobs.release(); ctx->h_item_start.release(); ctx->h_total.release();
+  ctx->r_counts.release(); ctx->r_offsets.release(); ctx->r_matches.release();
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return MVGCUDA_OK;
+}
+
+int mvgcuda_upload_images(mvgcuda_ctx* ctx, int n_images, const uint8_t* const* desc, const int32_t* rows, int pinned) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (n_images < 0 || (n_images > 0 && (!desc || !rows))) { ctx->set_error("bad image list"); return MVGCUDA_ERR_INVALID; }
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  ctx->feats.clear();
+  ctx->r_pairs = 0;
+  return fill_arena(ctx, ctx->images, n_images, desc, rows, pinned);
+}
+
+int mvgcuda_num_images(const mvgcuda_ctx* ctx) { return ctx ? (int)ctx->images.rows.size() : -1; }
+int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image) {
+  if (!ctx || image < 0 || image >= (int)ctx->images.rows.size()) return -1;
+  return ctx->images.rows[image];
+}
+
+int mvgcuda_knn2(mvgcuda_ctx* ctx, int db_img, int q_img, int tie_mode, int32_t* idx, float* dist) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  return knn2_impl(ctx, ctx->images, db_img, q_img, tie_mode, idx, dist);
+}
+
+int mvgcuda_knn2_arrays(mvgcuda_ctx* ctx, const uint8_t* db, int db_rows, const uint8_t* query, int q_rows,
+                        int tie_mode, int32_t* idx, float* dist) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (db_rows < 2 || q_rows < 1) { ctx->set_error("Too much asked nearest neighbors"); return MVGCUDA_ERR_INVALID; }
+  if (!db || !query) { ctx->set_error("null descriptor pointer"); return MVGCUDA_ERR_INVALID; }
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  const uint8_t* d[2] = {db, query};
+  const int32_t r[2] = {db_rows, q_rows};
+  int rc = fill_arena(ctx, ctx->scratch, 2, d, r, 0);
+  if (rc) return rc;
+  return knn2_impl(ctx, ctx->scratch, 0, 1, tie_mode, idx, dist);
+}
+
+int mvgcuda_match_pairs(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,
+                        mvgcuda_pair_matches* out) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  return match_pairs_impl(ctx, n_pairs, pairs, ratio_sq, out);
+}
+
+int mvgcuda_set_features(mvgcuda_ctx* ctx, int n_images, const float* const* feats_xy, const int32_t* rows) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (n_images != (int)ctx->images.rows.size()) { ctx->set_error("set_features: image count differs from uploaded set"); return MVGCUDA_ERR_INVALID; }
+  for (int i = 0; i < n_images; ++i)
+    if (rows[i] != ctx->images.rows[i] || (rows[i] > 0 && !feats_xy[i])) { ctx->set_error("set_features: image %d rows mismatch", i); return MVGCUDA_ERR_INVALID; }
+  ctx->feats.resize(n_images);
+  for (int i = 0; i < n_images; ++i) ctx->feats[i].assign(feats_xy[i], feats_xy[i] + 2 * (size_t)rows[i]);
+  return MVGCUDA_OK;
+}
+
+int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,
+                             int host_threads, mvgcuda_pair_matches* out) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (ctx->feats.size() != ctx->images.rows.size()) { ctx->set_error("match_collection: call mvgcuda_set_features first"); return MVGCUDA_ERR_INVALID; }
+  mvgcuda_pair_matches raw;
+  int rc = match_pairs_impl(ctx, n_pairs, pairs, ratio_sq, &raw);
+  if (rc) return rc;
+  if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  host_threads = (int)std::min<int64_t>(host_threads, std::max<int64_t>(n_pairs, 1));
+  std::vector<std::vector<int>> per_pair(n_pairs);
+  std::atomic<int64_t> cursor{0};
+  auto work = [&]() {
+    std::vector<int> tmp;
+    for (;;) {
+      const int64_t p = cursor.fetch_add(1);
+      if (p >= n_pairs) break;
+      const int I = pairs[2 * p], J = pairs[2 * p + 1];
+      dedup_xy(ctx->feats[I].data(), ctx->feats[J].data(), raw.matches + 2 * raw.offsets[p], raw.counts[p], tmp);
+      per_pair[p] = tmp;
+    }
+  };
+  if (host_threads == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < host_threads; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  ctx->c_counts.resize(n_pairs);
+  ctx->c_offsets.resize(n_pairs + 1);
+  long long tot = 0;
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    ctx->c_counts[p] = (int)per_pair[p].size() / 2;
+    ctx->c_offsets[p] = tot;
+    tot += ctx->c_counts[p];
+  }
+  ctx->c_offsets[n_pairs] = tot;
+  ctx->c_matches.resize((size_t)tot * 2);
+  for (int64_t p = 0; p < n_pairs; ++p)
+    if (!per_pair[p].empty())
+      memcpy(&ctx->c_matches[2 * ctx->c_offsets[p]], per_pair[p].data(), per_pair[p].size() * sizeof(int));
+  ctx->last_was_collection = true;
+  if (out) {
+    *out = raw;
+    out->counts = ctx->c_counts.data();
+    out->offsets = reinterpret_cast<const int64_t*>(ctx->c_offsets.data());
+    out->matches = ctx->c_matches.data();
+  }
+  return MVGCUDA_OK;
+}
+
+int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* path) {
+  if (!ctx || !pairs || !path) return MVGCUDA_ERR_INVALID;
+  const int64_t n = ctx->r_pairs;
+  const int* counts = ctx->last_was_collection ? ctx->c_counts.data() : ctx->r_counts.p;
+  const long long* offs = ctx->last_was_collection ? ctx->c_offsets.data() : ctx->r_offsets.p;
+  const int* m = ctx->last_was_collection ? ctx->c_matches.data() : ctx->r_matches.p;
+  // std::map<pair<size_t,size_t>,...> iteration order; map::insert keeps the FIRST of duplicate keys
+  std::vector<int64_t> order(n);
+  for (int64_t p = 0; p < n; ++p) order[p] = p;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    if (pairs[2 * a] != pairs[2 * b]) return pairs[2 * a] < pairs[2 * b];
+    return pairs[2 * a + 1] < pairs[2 * b + 1];
+  });
+  FILE* f = fopen(path, "wb");
+  if (!f) { ctx->set_error("cannot open %s for writing", path); return MVGCUDA_ERR_IO; }
+  std::string buf;
+  buf.reserve(1 << 20);
+  char line[64];
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t p = order[k];
+    if (k > 0 && pairs[2 * p] == pairs[2 * order[k - 1]] && pairs[2 * p + 1] == pairs[2 * order[k - 1] + 1]) continue;
+    int len = snprintf(line, sizeof line, "%d %d\n%d\n", pairs[2 * p], pairs[2 * p + 1], counts[p]);
+    buf.append(line, len);
+    const int* mm = m + 2 * offs[p];
+    for (int c = 0; c < counts[p]; ++c) {
+      len = snprintf(line, sizeof line, "%d %d\n", mm[2 * c], mm[2 * c + 1]);
+      buf.append(line, len);
+    }
+    if (buf.size() > (1 << 20) - 4096) {
+      if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); ctx->set_error("short write to %s", path); return MVGCUDA_ERR_IO; }
+      buf.clear();
+    }
+  }
+  const bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  if (fclose(f) != 0 || !ok) { ctx->set_error("short write to %s", path); return MVGCUDA_ERR_IO; }
+  return MVGCUDA_OK;
+}
+
+int mvgcuda_get_device_info(const mvgcuda_ctx* ctx, mvgcuda_device_info* out) {
+  if (!ctx || !out) return MVGCUDA_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  snprintf(out->name, sizeof out->name, "%s", ctx->prop.name);
+  out->sm_count = ctx->prop.multiProcessorCount;
+  out->cc_major = ctx->prop.major;
+  out->cc_minor = ctx->prop.minor;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+  out->clock_khz = khz;
+  out->hbm_bytes = (int64_t)ctx->prop.totalGlobalMem;
+  return MVGCUDA_OK;
+}
+
+int mvgcuda_probe_i8_peak(mvgcuda_ctx* ctx, int iters, double* ops_per_sec, float* ms_out) {
+  if (!ctx || iters < 1) return MVGCUDA_ERR_INVALID;
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int grid = ctx->prop.multiProcessorCount;
+  const size_t smem = kBytesA + kBytesB + 1024;
+  cudaStream_t st = ctx->stream;
+  i8_peak_probe_kernel<<<grid, 128, smem, st>>>(iters);  // warm-up
+  CU_CHECK(ctx, cudaGetLastError());
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], st));
+  i8_peak_probe_kernel<<<grid, 128, smem, st>>>(iters);
+  CU_CHECK(ctx, cudaGetLastError());
+  CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));
+  CU_CHECK(ctx, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  if (ms_out) *ms_out = ms;
+  if (ops_per_sec) *ops_per_sec = 2.0 * kBlockQ * kTileDb * 32.0 * (double)iters * grid / (ms * 1e-3);
+  return MVGCUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+"""ctypes binding of libmvgcuda (include/mvgcuda.h) plus the Python mirror of the reference's matcher
+interfaces for this path.
+
+Mirrors (reference file:line, relative to the reference tree):
+  * ``ArrayMatcherCuda``       <-> ArrayMatcher<uchar,Metric>   libs/feature/include/mvg/feature/matching_interface.h:16-64
+                                    (BF implementation: matcher_brute_force.h:42-50,102-134)
+  * ``MatcherCudaAllInMemory`` <-> MatcherAllInMemory            matcher_all_in_memory.h:19-147
+  * ``square_f32``             <-> Square(float)                 libs/base/include/mvg/math/numeric.h:108-111
+
+There is NO CPU fallback here: if the shared library is missing, or no sm_100 device is present,
+every compute call raises ``MvgCudaError``.  (The CPU oracle lives under ``oracle/`` and is test
+infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+DIM = 128
+TIE_LOWEST_INDEX = 0
+TIE_REFERENCE = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvgcuda.so")
+
+
+class MvgCudaError(RuntimeError):
+    pass
+
+
+class _PairMatches(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int64),
+        ("counts", C.POINTER(C.c_int32)),
+        ("offsets", C.POINTER(C.c_int64)),
+        ("matches", C.POINTER(C.c_int32)),
+        ("gpu_ms", C.c_float),
+        ("knn_kernel_ms", C.c_float),
+        ("knn_kernel_launches", C.c_int32),
+        ("total_launches", C.c_int32),
+    ]
+
+
+class _DeviceInfo(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 128),
+        ("sm_count", C.c_int),
+        ("cc_major", C.c_int),
+        ("cc_minor", C.c_int),
+        ("clock_khz", C.c_int),
+        ("hbm_bytes", C.c_int64),
+    ]
+
+
+# every symbol include/mvgcuda.h declares: name -> (restype, argtypes)
+_u8pp = C.POINTER(C.POINTER(C.c_uint8))
+_f32pp = C.POINTER(C.POINTER(C.c_float))
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_ctx = C.c_void_p
+ABI: Dict[str, Tuple[object, list]] = {
+    "mvgcuda_version": (C.c_int, []),
+    "mvgcuda_device_count": (C.c_int, []),
+    "mvgcuda_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),
+    "mvgcuda_destroy": (None, [_ctx]),
+    "mvgcuda_last_error": (C.c_char_p, [_ctx]),
+    "mvgcuda_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "mvgcuda_upload_images": (C.c_int, [_ctx, C.c_int, _u8pp, _i32p, C.c_int]),
+    "mvgcuda_num_images": (C.c_int, [_ctx]),
+    "mvgcuda_image_rows": (C.c_int, [_ctx, C.c_int]),
+    "mvgcuda_knn2": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _f32p]),
+    "mvgcuda_knn2_arrays": (C.c_int, [_ctx, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, _i32p, _f32p]),
+    "mvgcuda_match_pairs": (C.c_int, [_ctx, C.c_int64, _i32p, C.c_float, C.POINTER(_PairMatches)]),
+    "mvgcuda_set_features": (C.c_int, [_ctx, C.c_int, _f32pp, _i32p]),
+    "mvgcuda_match_collection": (C.c_int, [_ctx, C.c_int64, _i32p, C.c_float, C.c_int, C.POINTER(_PairMatches)]),
+    "mvgcuda_export_matches": (C.c_int, [_ctx, _i32p, C.c_char_p]),
+    "mvgcuda_get_device_info": (C.c_int, [_ctx, C.POINTER(_DeviceInfo)]),
+    "mvgcuda_probe_i8_peak": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), _f32p]),
+}
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen libmvgcuda.so and bind every ABI symbol.  Raises MvgCudaError if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise MvgCudaError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def square_f32(r: float) -> np.float32:
+    """Square(float) of the reference (numeric.h:108-111): the product is rounded in fp32.
+    0.8 -> 0x3f23d70b, which is NOT float32(0.64)."""
+    f = np.float32(r)
+    return np.float32(f * f)
+
+
+def pairs_exhaustive(n_images: int) -> np.ndarray:
+    """(i, j), i < j, in the order of MatcherAllInMemory::Match's double loop (matcher_all_in_memory.h:71-90)."""
+    i, j = np.triu_indices(n_images, k=1)
+    return np.stack([i, j], axis=1).astype(np.int32)
+
+
+def _as_u8_matrix(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 2 or a.shape[1] != DIM:
+        raise ValueError(f"descriptors must be [rows][{DIM}] uint8, got {a.shape}")
+    return a
+
+
+class PairMatches:
+    """Result of a match call (copied out of the context's buffers)."""
+
+    def __init__(self, pairs: np.ndarray, counts: np.ndarray, offsets: np.ndarray, matches: np.ndarray, timing: dict):
+        self.pairs, self.counts, self.offsets, self.matches, self.timing = pairs, counts, offsets, matches, timing
+
+    def __len__(self) -> int:
+        return len(self.counts)
+
+    def pair(self, p: int) -> np.ndarray:
+        """[count][2] (_i, _j) of pair p."""
+        return self.matches[self.offsets[p]:self.offsets[p + 1]]
+
+    def as_dict(self) -> Dict[Tuple[int, int], np.ndarray]:
+        """PairWiseMatches (indexed_match.h:69): first insertion wins for duplicate keys, as std::map::insert."""
+        out: Dict[Tuple[int, int], np.ndarray] = {}
+        for p, (i, j) in enumerate(self.pairs):
+            out.setdefault((int(i), int(j)), self.pair(p))
+        return out
+
+
+class Context:
+    """One libmvgcuda context == one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = _ctx()
+        rc = self._lib.mvgcuda_create(device, C.byref(h))
+        if rc != 0:
+            raise MvgCudaError(f"mvgcuda_create({device}) failed [{rc}]: {self._lib.mvgcuda_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+        self._rows: List[int] = []
+
+    # -- plumbing
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mvgcuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise MvgCudaError(f"{what} failed [{rc}]: {self._lib.mvgcuda_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._lib.mvgcuda_set_stream(self._h, C.c_void_p(cuda_stream)), "mvgcuda_set_stream")
+
+    def device_info(self) -> dict:
+        di = _DeviceInfo()
+        self._check(self._lib.mvgcuda_get_device_info(self._h, C.byref(di)), "mvgcuda_get_device_info")
+        return {"name": di.name.decode(), "sm_count": di.sm_count, "cc": (di.cc_major, di.cc_minor),
+                "clock_khz": di.clock_khz, "hbm_bytes": di.hbm_bytes}
+
+    def probe_i8_peak(self, iters: int = 20000) -> Tuple[float, float]:
+        ops = C.c_double()
+        ms = C.c_float()
+        self._check(self._lib.mvgcuda_probe_i8_peak(self._h, iters, C.byref(ops), C.byref(ms)), "mvgcuda_probe_i8_peak")
+        return ops.value, ms.value
+
+    # -- residency
+    def upload_images(self, descs: Sequence[np.ndarray], pinned: bool = False) -> None:
+        mats = [_as_u8_matrix(d) if len(d) else np.zeros((0, DIM), np.uint8) for d in descs]
+        n = len(mats)
+        ptrs = (C.POINTER(C.c_uint8) * max(n, 1))()
+        rows = (C.c_int32 * max(n, 1))()
+        for k, m in enumerate(mats):
+            ptrs[k] = m.ctypes.data_as(C.POINTER(C.c_uint8)) if m.shape[0] else None
+            rows[k] = m.shape[0]
+        self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rows, int(pinned)), "mvgcuda_upload_images")
+        self._rows = [m.shape[0] for m in mats]
+
+    def set_features(self, feats_xy: Sequence[np.ndarray]) -> None:
+        mats = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy]
+        n = len(mats)
+        ptrs = (C.POINTER(C.c_float) * max(n, 1))()
+        rows = (C.c_int32 * max(n, 1))()
+        for k, m in enumerate(mats):
+            ptrs[k] = m.ctypes.data_as(C.POINTER(C.c_float)) if m.shape[0] else None
+            rows[k] = m.shape[0]
+        self._check(self._lib.mvgcuda_set_features(self._h, n, ptrs, rows), "mvgcuda_set_features")
+
+    # -- array level
+    def knn2(self, db_img: int, q_img: int, tie_mode: int = TIE_REFERENCE) -> Tuple[np.ndarray, np.ndarray]:
+        nq = self._rows[q_img] if 0 <= q_img < len(self._rows) else 0
+        idx = np.empty((max(nq, 1), 2), np.int32)
+        dist = np.empty((max(nq, 1), 2), np.float32)
+        self._check(self._lib.mvgcuda_knn2(self._h, db_img, q_img, tie_mode, idx.ctypes.data_as(_i32p),
+                                           dist.ctypes.data_as(_f32p)), "mvgcuda_knn2")
+        return idx[:nq], dist[:nq]
+
+    def knn2_arrays(self, db: np.ndarray, query: np.ndarray, tie_mode: int = TIE_REFERENCE) -> Tuple[np.ndarray, np.ndarray]:
+        db, query = _as_u8_matrix(db), _as_u8_matrix(query)
+        nq = query.shape[0]
+        idx = np.empty((max(nq, 1), 2), np.int32)
+        dist = np.empty((max(nq, 1), 2), np.float32)
+        u8p = C.POINTER(C.c_uint8)
+        self._check(self._lib.mvgcuda_knn2_arrays(self._h, db.ctypes.data_as(u8p), db.shape[0], query.ctypes.data_as(u8p), nq,
+                                                  tie_mode, idx.ctypes.data_as(_i32p), dist.ctypes.data_as(_f32p)),
+                    "mvgcuda_knn2_arrays")
+        return idx[:nq], dist[:nq]
+
+    # -- pair / collection level
+    def _collect(self, pairs: np.ndarray, pm: _PairMatches) -> PairMatches:
+        n = int(pm.n_pairs)
+        counts = np.ctypeslib.as_array(pm.counts, shape=(max(n, 1),))[:n].copy()
+        offsets = np.ctypeslib.as_array(pm.offsets, shape=(n + 1,)).copy()
+        total = int(offsets[n])
+        matches = (np.ctypeslib.as_array(pm.matches, shape=(max(total, 1) * 2,))[: total * 2].copy().reshape(total, 2))
+        timing = {"gpu_ms": pm.gpu_ms, "knn_kernel_ms": pm.knn_kernel_ms, "knn_kernel_launches": pm.knn_kernel_launches,
+                  "total_launches": pm.total_launches}
+        return PairMatches(pairs, counts, offsets, matches, timing)
+
+    def match_pairs(self, pairs: np.ndarray, ratio_sq: float, collect: bool = True):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        pm = _PairMatches()
+        self._check(self._lib.mvgcuda_match_pairs(self._h, len(pairs), pairs.ctypes.data_as(_i32p), C.c_float(ratio_sq),
+                                                  C.byref(pm)), "mvgcuda_match_pairs")
+        return self._collect(pairs, pm) if collect else pm
+
+    def match_collection(self, pairs: np.ndarray, ratio_sq: float, host_threads: int = 0, collect: bool = True):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        pm = _PairMatches()
+        self._check(self._lib.mvgcuda_match_collection(self._h, len(pairs), pairs.ctypes.data_as(_i32p), C.c_float(ratio_sq),
+                                                       host_threads, C.byref(pm)), "mvgcuda_match_collection")
+        return self._collect(pairs, pm) if collect else pm
+
+    def export_matches(self, pairs: np.ndarray, path: str) -> None:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        self._check(self._lib.mvgcuda_export_matches(self._h, pairs.ctypes.data_as(_i32p), path.encode()), "mvgcuda_export_matches")
+
+
+# ------------------------------------------------------------------------------------------------
+# Mirrors of the reference's operator interfaces (same names / argument meaning / error behaviour)
+
+
+class ArrayMatcherCuda:
+    """ArrayMatcher<unsigned char, SquaredEuclideanDistanceVectorized<unsigned char>> on the GPU.
+
+    ``Build`` copies the db to HBM (the reference's BF matcher borrows the pointer,
+    matcher_brute_force.h:47-48); ``SearchNeighbours`` APPENDS k (idx, dist) per query to the output
+    lists like the BF matcher (``push_back``, :128-131), returns False and reports
+    "Too much asked nearest neighbors" when k > rows or nq < 1 (:107-110).  Only k in {1, 2}.
+    """
+
+    def __init__(self, ctx: Optional[Context] = None, tie_mode: int = TIE_REFERENCE):
+        self._ctx = ctx or Context(0)
+        self._db: Optional[np.ndarray] = None
+        self._tie = tie_mode
+
+    def Build(self, dataset: np.ndarray, rows_num: int, dimension: int = DIM) -> bool:
+        if rows_num < 1:  # matcher_brute_force.h:43-46
+            self._db = None
+            return False
+        if dimension != DIM:
+            raise ValueError("ArrayMatcherCuda handles 128-byte descriptors only")
+        self._db = _as_u8_matrix(np.asarray(dataset).reshape(-1, DIM)[:rows_num]).copy()
+        return True
+
+    def SearchNeighbours(self, query: np.ndarray, query_num: int, vec_indice: list, vec_distance: list,
+                         nearest_neighbor_num: int = 2) -> bool:
+        rows = 0 if self._db is None else self._db.shape[0]
+        if nearest_neighbor_num > rows or query_num < 1:
+            import sys
+            print("Too much asked nearest neighbors", file=sys.stderr)
+            return False
+        if nearest_neighbor_num not in (1, 2):
+            raise ValueError("ArrayMatcherCuda accelerates k = 1 or 2 only")
+        q = _as_u8_matrix(np.asarray(query).reshape(-1, DIM)[:query_num])
+        db = self._db
+        if rows == 1:  # k == 1 against a single row: duplicate it so the 2-NN kernel has two candidates
+            db = np.concatenate([db, db], axis=0)
+        idx, dist = self._ctx.knn2_arrays(db, q, self._tie)
+        k = nearest_neighbor_num
+        if rows == 1:
+            idx = np.zeros_like(idx)
+        vec_indice.extend(idx[:, :k].reshape(-1).tolist())
+        vec_distance.extend(dist[:, :k].reshape(-1).tolist())
+        return True
+
+    def SearchNeighbour(self, query: np.ndarray) -> Tuple[bool, int, float]:
+        """Single nearest neighbour (matcher_brute_force.h:61-89: std::min_element => lowest index on ties)."""
+        if self._db is None:
+            return False, -1, 0.0
+        db = self._db if self._db.shape[0] > 1 else np.concatenate([self._db, self._db], axis=0)
+        idx, dist = self._ctx.knn2_arrays(db, _as_u8_matrix(np.asarray(query).reshape(1, DIM)), TIE_LOWEST_INDEX)
+        return True, (int(idx[0, 0]) if self._db.shape[0] > 1 else 0), float(dist[0, 0])
+
+
+class MatcherCudaAllInMemory:
+    """MatcherAllInMemory<KeypointSet<ScalePointFeature, Descriptor<uchar,128>>, ArrayMatcherBruteForce<...>>.
+
+    ``LoadData(file_names, match_dir)`` reads ``<match_dir>/<basename>.feat`` (text, feature.h:117-133) and
+    ``.desc`` (binary, descriptor.h:160-181; 8-byte count as written on Linux, or the 4-byte count of the
+    shipped data/et files) and makes them resident in HBM; ``Match(file_names)`` returns the PairWiseMatches
+    dict {(i, j): [count][2]} for every i < j, empty pairs included (matcher_all_in_memory.h:135).
+    """
+
+    def __init__(self, distRatio: float, ctx: Optional[Context] = None, host_threads: int = 0):
+        self.distance_ratio = np.float32(distRatio)
+        self._ctx = ctx or Context(0)
+        self._threads = host_threads
+        self._n = 0
+
+    def LoadArrays(self, descs: Sequence[np.ndarray], feats_xy: Sequence[np.ndarray]) -> bool:
+        # row counts come from the features, as in the reference (matcher_all_in_memory.h:80,85,107)
+        rows = [np.asarray(f).reshape(-1, 2).shape[0] for f in feats_xy]
+        d2 = []
+        for d, r in zip(descs, rows):
+            d = np.asarray(d, dtype=np.uint8).reshape(-1, DIM)
+            if d.shape[0] < r:
+                raise MvgCudaError(".feat has more rows than .desc (the reference over-reads here; refused)")
+            d2.append(d[:r])
+        self._ctx.upload_images(d2)
+        self._ctx.set_features(feats_xy)
+        self._n = len(d2)
+        return True
+
+    def LoadData(self, file_names: Sequence[str], match_dir: str) -> bool:
+        from .io import load_descs_bin, load_feats
+        descs, feats = [], []
+        for name in file_names:
+            base = os.path.splitext(os.path.basename(name))[0]
+            feats.append(load_feats(os.path.join(match_dir, base + ".feat"))[:, :2])
+            descs.append(load_descs_bin(os.path.join(match_dir, base + ".desc")))
+        return self.LoadArrays(descs, feats)
+
+    def Match(self, file_names: Optional[Sequence[str]] = None, pairs: Optional[np.ndarray] = None) -> Dict[Tuple[int, int], np.ndarray]:
+        n = self._n if file_names is None else len(file_names)
+        if pairs is None:
+            pairs = pairs_exhaustive(n)
+        self.last = self._ctx.match_collection(pairs, float(square_f32(self.distance_ratio)), self._threads)
+        return self.last.as_dict()
+
+    def Export(self, path: str) -> None:
+        """matches.putative.txt, byte-identical to PairedIndexedMatchToStream (indexed_match_utils.h:22-38)."""
+        self._ctx.export_matches(self.last.pairs, path)

@@ -1,0 +1,171 @@
+/*
+ * mvgcuda.h -- C ABI of libmvgcuda: B200 (sm_100a) exhaustive putative matching of
+ * uint8 SIFT-128 descriptors (brute-force squared-L2 2-NN + Lowe ratio test).
+ *
+ * This is the drop-in boundary for ONE hot path of yueying/3DReconstruction.  The reference
+ * has no FFI of its own (it is header-only C++ templates); every entry point below names the
+ * reference interface it stands in for.  Citations are relative to the reference tree.
+ *
+ *   array level      ArrayMatcher<uchar,Metric>::Build / SearchNeighbours
+ *                    libs/feature/include/mvg/feature/matching_interface.h:16-64
+ *                    libs/feature/include/mvg/feature/matcher_brute_force.h:42-50,102-134
+ *   collection level MatcherAllInMemory::LoadData / Match
+ *                    libs/feature/include/mvg/feature/matcher_all_in_memory.h:44-60,62-141
+ *   filters          DistanceRatioFilter  matching_filters.h:27-47
+ *                    IndexedMatch::getDeduplicated  indexed_match.h:49-55
+ *                    IndexedMatchDecorator::getDeduplicated  indexed_match_decorator.h:90-104
+ *   export           PairedIndexedMatchToStream  indexed_match_utils.h:22-38
+ *
+ * Conventions: plain C symbols, every function returns an int status (0 = MVGCUDA_OK), no
+ * exception crosses the boundary, all buffers are caller-owned unless stated, a context is
+ * bound to ONE GPU and may be used from one host thread at a time (use one context per GPU).
+ * Descriptors are dense row-major [rows][128] uint8 (== std::vector<Descriptor<uchar,128>>,
+ * descriptor.h:23-58).  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with MVGCUDA_ERR_CUDA.
+ */
+#ifndef MVGCUDA_H_
+#define MVGCUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVGCUDA_DIM 128 /* descriptor length, Descriptor<unsigned char,128> (compute_matches.cpp:182-186) */
+
+enum mvgcuda_status {
+  MVGCUDA_OK = 0,
+  MVGCUDA_ERR_INVALID = 1, /* bad argument (null pointer, negative size, unknown image id ...) */
+  MVGCUDA_ERR_CUDA = 2,    /* CUDA runtime/driver failure, or no sm_100 device */
+  MVGCUDA_ERR_NOMEM = 3,   /* host or device allocation failed */
+  MVGCUDA_ERR_IO = 4       /* file could not be written */
+};
+
+/* How raw 2-NN indices are chosen when distances tie (matcher_brute_force.h:124-131 +
+ * indexed_sort.h:52-66).  Exported MATCHES never depend on this (a tie d1==d2 never passes
+ * the ratio test for ratio <= 1, matching_filters.h:44). */
+enum mvgcuda_tie_mode {
+  MVGCUDA_TIE_LOWEST_INDEX = 0, /* smallest db row wins (BASELINE.json north_star wording) */
+  MVGCUDA_TIE_REFERENCE = 1     /* reproduce libstdc++ std::partial_sort(…,2) as used by
+                                   SortIndexHelper: bit-identical raw indices */
+};
+
+typedef struct mvgcuda_ctx mvgcuda_ctx;
+
+/* Library/ABI version (major*10000 + minor*100 + patch). */
+int mvgcuda_version(void);
+
+/* Number of visible CUDA devices with compute capability 10.x (0 if none / no driver). */
+int mvgcuda_device_count(void);
+
+/* Create a context on CUDA device `device`.  Fails (MVGCUDA_ERR_CUDA) unless it is sm_100. */
+int mvgcuda_create(int device, mvgcuda_ctx** out);
+void mvgcuda_destroy(mvgcuda_ctx* ctx);
+
+/* Last error text of this context (never NULL; "" when no error).  With ctx == NULL returns the
+ * text of the last mvgcuda_create failure on this thread. */
+const char* mvgcuda_last_error(const mvgcuda_ctx* ctx);
+
+/* Run the context's work on an externally owned CUDA stream (cudaStream_t as void*), e.g.
+ * torch.cuda.current_stream().cuda_stream, so that the caller's CUDA events bracket the kernels.
+ * NULL restores the context's own stream. */
+int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Residency: copy n_images descriptor arrays into the context's HBM arena (replaces the
+ * map_descriptors residency of MatcherAllInMemory::LoadData, matcher_all_in_memory.h:44-60,
+ * and ArrayMatcherBruteForce::Build, matcher_brute_force.h:42-50 -- but COPIES, so the caller
+ * may free its buffers).  Replaces any previously uploaded set.  rows[i] >= 0; desc[i] may be
+ * NULL when rows[i] == 0.  Also runs the per-row squared-norm kernel.
+ * `pinned` != 0 promises that the desc buffers are page-locked (async H2D). */
+int mvgcuda_upload_images(mvgcuda_ctx* ctx, int n_images, const uint8_t* const* desc,
+                          const int32_t* rows, int pinned);
+int mvgcuda_num_images(const mvgcuda_ctx* ctx);
+int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image); /* <0 on bad id */
+
+/* ------------------------------------------------------------------------------------------
+ * Array level: 2 nearest neighbours of every row of image q_img among the rows of image
+ * db_img == ArrayMatcherBruteForce<uchar,SquaredEuclideanDistanceVectorized<uchar>>::
+ * SearchNeighbours(query, nq, &idx, &dist, 2)  (matcher_brute_force.h:102-134, metric.h:51-82).
+ * idx/dist are [nq][2], distances ascending; dist holds exact integers as float (max
+ * 128*255^2 < 2^24).  Returns MVGCUDA_ERR_INVALID when db rows < 2 or nq < 1 -- the reference
+ * prints "Too much asked nearest neighbors" and returns false (matcher_brute_force.h:107-110). */
+int mvgcuda_knn2(mvgcuda_ctx* ctx, int db_img, int q_img, int tie_mode, int32_t* idx, float* dist);
+
+/* Same, on caller arrays (Build + SearchNeighbours in one call; uses a scratch slot of the
+ * context, the uploaded image set is left untouched). */
+int mvgcuda_knn2_arrays(mvgcuda_ctx* ctx, const uint8_t* db, int db_rows, const uint8_t* query,
+                        int q_rows, int tie_mode, int32_t* idx, float* dist);
+
+/* ------------------------------------------------------------------------------------------
+ * Pair level: for each pair (I=pairs[2p], J=pairs[2p+1]) run, on the GPU,
+ *   SearchNeighbours(J against I, k=2)                       matcher_all_in_memory.h:107
+ *   DistanceRatioFilter(..., ratio_sq)                        :111-115  (fp32: d1 < ratio_sq*d2)
+ *   the drop-last loop (last passing query discarded)         :117-122
+ *   IndexedMatch::getDeduplicated (unique on consecutive _i)  :125
+ * and return per pair the surviving (_i,_j) in ascending _j.  ratio_sq must be the fp32 value
+ * the reference computes, Square(float distRatio) (numeric.h:108-111): pass r*r evaluated in
+ * float, NOT float(double(r)*r).  Pairs whose images have < 2 db rows or < 1 query rows yield
+ * zero matches (reference: SearchNeighbours returns false / empty, Appendix B of SURVEY.md).
+ *
+ * Result storage is owned by the context and valid until the next match_* / upload / destroy:
+ *   counts[p]            matches of pair p
+ *   offsets[p]           start of pair p in `matches` (in matches, not bytes); offsets[n_pairs]=total
+ *   matches[2*k+0/1]     _i (row in I), _j (row in J)
+ */
+typedef struct mvgcuda_pair_matches {
+  int64_t n_pairs;
+  const int32_t* counts;
+  const int64_t* offsets;
+  const int32_t* matches;
+  /* device time of the GPU work of this call (CUDA events on the context's stream), ms */
+  float gpu_ms;
+  /* of which the fused distance/top-2 kernel */
+  float knn_kernel_ms;
+  int32_t knn_kernel_launches;
+  int32_t total_launches;
+} mvgcuda_pair_matches;
+
+int mvgcuda_match_pairs(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,
+                        mvgcuda_pair_matches* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Collection level == MatcherAllInMemory<KeypointSet<ScalePointFeature,Descriptor<uchar,128>>,
+ * ArrayMatcherBruteForce<...>>::Match  (matcher_all_in_memory.h:62-141) restricted to the given
+ * pair list: match_pairs as above, then on a host worker pool the coordinate de-duplication
+ * IndexedMatchDecorator<float>::getDeduplicated (indexed_match_decorator.h:33-53,90-104; same
+ * comparator, same std::set) using the features' (x,y).  feats_xy[i] is [rows_i][2] float
+ * (x,y of ScalePointFeature, feature.h:79-113) for every uploaded image.
+ * Result layout as for match_pairs (order within a pair is the std::set iteration order). */
+int mvgcuda_set_features(mvgcuda_ctx* ctx, int n_images, const float* const* feats_xy,
+                         const int32_t* rows);
+int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs,
+                             float ratio_sq, int host_threads, mvgcuda_pair_matches* out);
+
+/* Write the result of the last match_pairs / match_collection call in the reference's text format
+ * "i j\ncount\n_i _j\n..." in lexicographic (i,j) order == PairedIndexedMatchToStream
+ * (indexed_match_utils.h:22-38).  `pairs` must be the list given to that call. */
+int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* path);
+
+/* ------------------------------------------------------------------------------------------
+ * Instrumentation. */
+typedef struct mvgcuda_device_info {
+  char name[128];
+  int sm_count;
+  int cc_major, cc_minor;
+  int clock_khz;
+  int64_t hbm_bytes;
+} mvgcuda_device_info;
+int mvgcuda_get_device_info(const mvgcuda_ctx* ctx, mvgcuda_device_info* out);
+
+/* Tensor-pipe ceiling probe: issue `iters` back-to-back tcgen05.mma kind::i8 M128xN256xK32
+ * instructions per CTA on every SM with no loads and no epilogue; returns achieved int8 op/s
+ * (2 ops per MAC).  Used by bench.py as the measured int8 roofline denominator. */
+int mvgcuda_probe_i8_peak(mvgcuda_ctx* ctx, int iters, double* ops_per_sec, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVGCUDA_H_ */
