@@ -1,0 +1,118 @@
+"""Host-side logic that needs no GPU: file formats, pair enumeration, the multi-GPU pair scheduler (incl. a
+world_size-2 gloo run), synthetic generator determinism."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sharding = importlib.import_module("3dreconstruction_b200.sharding")
+pkg_io = importlib.import_module("3dreconstruction_b200.io")
+synth = importlib.import_module("3dreconstruction_b200.synth")
+
+
+def test_desc_roundtrip_both_headers(tmp_path):
+    d = synth.uniform_set(1, 37)
+    for hdr in (8, 4):
+        p = str(tmp_path / f"a{hdr}.desc")
+        pkg_io.save_descs_bin(p, d, hdr)
+        assert os.path.getsize(p) == hdr + 37 * 128
+        assert np.array_equal(pkg_io.load_descs_bin(p), d)
+    assert pkg_io.load_descs_bin(str(tmp_path / "missing.desc")).shape == (0, 128)
+
+
+def test_feat_text_roundtrip(tmp_path):
+    f = synth.features(3, 0, 50)
+    p = str(tmp_path / "a.feat")
+    pkg_io.save_feats(p, f)
+    assert np.array_equal(pkg_io.load_feats(p), f)      # 6 significant digits survive the text round trip
+    assert open(p).readline().count(" ") == 3
+
+
+def test_matches_text_roundtrip(et):
+    from conftest import GOLDEN
+    txt = open(os.path.join(GOLDEN, "et_putative_r0.8.txt")).read()
+    pw = pkg_io.matches_from_text(txt)
+    assert len(pw) == 36 and pkg_io.matches_to_text(pw) == txt
+    assert "0 1\n" in txt and list(pw)[0] == (0, 1)
+
+
+def test_pairs_exhaustive_order(pkg):
+    p = pkg.pairs_exhaustive(4)
+    assert p.tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]]
+    assert len(pkg.pairs_exhaustive(100)) == 4950
+
+
+def test_shard_bounds_cover_and_balance(pkg):
+    rows = [10000] * 100
+    pairs = pkg.pairs_exhaustive(100)
+    for world in (1, 2, 4, 8):
+        got = [sharding.shard_pairs(pairs, rows, r, world) for r in range(world)]
+        assert np.array_equal(np.concatenate([g[0] for g in got]), pairs)
+        sizes = [len(g[0]) for g in got]
+        assert max(sizes) - min(sizes) <= 1
+    # ragged images: cost-balanced, contiguous, complete
+    rng = np.random.default_rng(0)
+    rows = rng.integers(0, 40000, 50).tolist()
+    pairs = pkg.pairs_exhaustive(50)
+    costs = sharding.pair_costs(pairs, rows)
+    b = sharding.shard_bounds(costs, 8)
+    assert b[0] == 0 and b[-1] == len(pairs) and all(x <= y for x, y in zip(b, b[1:]))
+    per = [costs[b[k]:b[k + 1]].sum() for k in range(8)]
+    assert max(per) <= costs.sum() / 8 + costs.max()
+
+
+def test_weak_scaling_collection_sizes():
+    assert [sharding.images_for_pairs_per_gpu(w) for w in (1, 2, 4, 8)] == [100, 142, 200, 282]
+
+
+def test_synth_deterministic_and_sift_like():
+    a = synth.collection(3, 3, 2000)
+    b = synth.collection(3, 3, 2000)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    norms = np.linalg.norm(a[0].astype(np.float64), axis=1)
+    assert 480 < norms.mean() < 530 and a[0].max() <= 255
+    assert 0.04 < (a[0] == 0).mean() < 0.2
+
+
+_GLOO_WORKER = r'''
+import importlib, os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MVG_ROOT"])
+pkg = importlib.import_module("3dreconstruction_b200")
+sharding = importlib.import_module("3dreconstruction_b200.sharding")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rows = [1000 + 10 * k for k in range(30)]
+pairs = pkg.pairs_exhaustive(30)
+mine, (b, e) = sharding.shard_pairs(pairs, rows, rank, world)
+# every rank reports (count, checksum); the union must be the whole list with no overlap
+t = torch.tensor([len(mine), int(mine.astype(np.int64).sum()), b, e], dtype=torch.int64)
+out = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(out, t)
+ms = torch.tensor([float(rank + 1)])
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # the "max over ranks" timing reduction bench.py uses
+if rank == 0:
+    print(json.dumps({"parts": [o.tolist() for o in out], "total": len(pairs), "sum": int(pairs.astype(np.int64).sum()), "max": ms.item()}))
+dist.destroy_process_group()
+'''
+
+
+def test_shard_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MVG_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert sum(p[0] for p in r["parts"]) == r["total"] and sum(p[1] for p in r["parts"]) == r["sum"]
+    assert r["parts"][0][3] == r["parts"][1][2] and r["parts"][0][2] == 0 and r["parts"][1][3] == r["total"]
+    assert r["max"] == 2.0
