@@ -12,6 +12,17 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef MVGCUDA_EXPERIMENT
+#define MVGCUDA_EXPERIMENT 0  // developer probes only (see epi_chunk16); 0 = the product
+#endif
+#if MVGCUDA_EXPERIMENT == 3
+__device__ unsigned long long g_dbg[8];  // [0] chunks, [1] slow chunks, [2] group hits, [3] lane hits (chunk level)
+__device__ __forceinline__ unsigned int* dbg_smem() { __shared__ unsigned int a[8]; return a; }
+#define DBG_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&dbg_smem()[i], (unsigned int)(v)); } while (0)
+#else
+#define DBG_ADD(i, v) do { } while (0)
+#endif
+
 namespace mvgcuda {
 
 constexpr int kDim = 128;      // descriptor bytes == GEMM K
@@ -26,10 +37,14 @@ constexpr int kPadNorm = 0x7FFFFF;  // "norm" of padding rows: > 128*255^2, so t
 
 constexpr uint32_t kBytesA = kBlockQ * kDim;        // 16 KB
 constexpr uint32_t kBytesB = kTileDb * kDim;        // 32 KB
-constexpr uint32_t kBytesC = kTileDb * sizeof(int); // 1 KB
+constexpr int kChunk = 16;                     // db rows per filter decision in the epilogue
+constexpr int kTileC = kTileDb + kTileDb / kChunk;  // per-tile constants: 256 packed (norm<<8|col) + 16 chunk-min norms
+constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
 
-constexpr int kNumEpiWarps = 4;
-constexpr int kKnnThreads = 128 + 32 * kNumEpiWarps;  // warps 0..3: TMA, MMA, TMEM-alloc, spare; 4..7 epilogue
+constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant: they share 32 queries and split each tile's columns
+constexpr int kNumEpiWarps = 4 * kEpiParts;
+constexpr int kPartCols = kTileDb / kEpiParts;        // 64 columns of every tile per warp
+constexpr int kKnnThreads = 128 + 32 * kNumEpiWarps;  // warps 0..3: TMA, MMA, TMEM-alloc, spare; 4.. epilogue
 
 struct PairJob {
   int db_row0;  // arena row of image I (db), multiple of kRowAlign
@@ -48,16 +63,18 @@ struct KnnRecord {  // one per query
 struct KnnSmem {
   alignas(1024) uint8_t a[kSlotsA][kBytesA];
   alignas(1024) uint8_t b[kStagesB][kBytesB];
-  alignas(16) int c[kSlotsC][kTileDb];
+  alignas(16) int c[kSlotsC][kTileC];
   uint64_t a_full[kSlotsA], a_empty[kSlotsA];
   uint64_t b_full[kStagesB], b_empty[kStagesB];
   uint64_t c_full[kSlotsC], c_empty[kSlotsC];
   uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
   uint32_t tmem_base;
+  int bound[2][kBlockQ];  // per (item parity, query): best-known 2nd-smallest t, atomically tightened by all parts
+  alignas(16) int4 xchg[2][kEpiParts - 1][kBlockQ];  // parts 1.. hand their top-2 to part 0 at the end of an item
 };
 
 struct KnnParams {
-  const int* __restrict__ ccol;        // K1 output, [arena_rows]
+  const int* __restrict__ ccol;        // K1 output, [arena_rows / 256][kTileC]
   const PairJob* __restrict__ jobs;    // [n_jobs]
   const int* __restrict__ item_start;  // [n_jobs+1] prefix sum of query blocks per job
   int n_jobs;
@@ -66,14 +83,16 @@ struct KnnParams {
 };
 
 // ------------------------------------------------------------------------------------------ K1
-// 8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles.
-__global__ void row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img_row0,
-                                  const int* __restrict__ img_rows, int n_images, int arena_rows,
-                                  int* __restrict__ ccol) {
-  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int row = static_cast<int>(gtid >> 3);
-  const int part = static_cast<int>(gtid & 7);
-  if (row >= arena_rows) return;  // whole 8-lane groups leave together (arena_rows*8 % 8 == 0)
+// Per-row constants, laid out per 256-row tile as [256 x ((||d||^2 << 8) | col)] [16 x min ||d||^2 of each 16-row chunk].
+// 8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles; 32 rows (2 chunks) per block.
+__device__ __forceinline__ int ccol_index(int row) { return (row >> 8) * kTileC + (row & 255); }
+
+__global__ void __launch_bounds__(256)
+row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img_row0, const int* __restrict__ img_rows,
+                  int n_images, int arena_rows, int* __restrict__ ccol) {
+  __shared__ int norms[32];
+  const int row = blockIdx.x * 32 + (threadIdx.x >> 3);  // arena_rows is a multiple of 256
+  const int part = threadIdx.x & 7;
   const uint4 v = *reinterpret_cast<const uint4*>(arena + (size_t)row * kDim + part * 16);
   unsigned s = 0;
   s = __dp4a(v.x, v.x, s);
@@ -92,7 +111,16 @@ __global__ void row_consts_kernel(const uint8_t* __restrict__ arena, const int* 
     }
     const bool real = n_images > 0 && (row - img_row0[lo]) < img_rows[lo];
     const int norm = real ? static_cast<int>(s) : kPadNorm;
-    ccol[row] = (norm << 8) | (row & 255);
+    norms[threadIdx.x >> 3] = norm;
+    ccol[ccol_index(row)] = (norm << 8) | (row & 255);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    int m = norms[threadIdx.x * 16];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) m = min(m, norms[threadIdx.x * 16 + k]);
+    const int row0 = blockIdx.x * 32 + threadIdx.x * 16;
+    ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = m;
   }
 }
 
@@ -113,16 +141,74 @@ __device__ __forceinline__ void top2_insert(int& l1, int& l2, int p) {
   l1 = min(l1, p);
 }
 
-__device__ __forceinline__ void epi_chunk(const int32_t (&v)[32], const int* __restrict__ cs, int& l1, int& l2) {
+// Sorted pair (lo <= hi) helpers for the exact top-2 of a chunk: a merge tree has depth ~10 and plenty of
+// instruction-level parallelism, where 16 serial insertions form a 32-deep dependency chain.
+struct Pair2 { int lo, hi; };
+__device__ __forceinline__ Pair2 sort2(int a, int b) { return Pair2{min(a, b), max(a, b)}; }
+__device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
+  return Pair2{min(a.lo, b.lo), __vimin3_s32(max(a.lo, b.lo), a.hi, b.hi)};
+}
+
+// One filter step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot products x = q.d:
+//   some row of the chunk can still enter the top-2  =>  min_norm(chunk) - 2*max(x) <= T   (T: best-known 2nd-smallest
+//   t = ||d||^2 - 2 q.d of this query, ties admitted).  10 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
+//   shared-memory traffic.  Only when some lane of the warp passes is the chunk examined in groups of 4, and only for the
+//   groups that pass are exact packed keys ((||d||^2 - 2x) << 8 | col, one IMAD each) formed and merged (top-2 of 4 by
+//   a small sorting network) into the tile's running top-2.
+// Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
+// by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
+__device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
+                                            const int g1t, const uint32_t bound_saddr, int& l1, int& l2, int& T) {
+#if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
+  l1 = min(l1, x[0]);
+  return;
+#endif
+  int g[4];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const int4 cc = *reinterpret_cast<const int4*>(cs + j);  // warp-uniform address: smem broadcast
-    top2_insert(l1, l2, static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(v[j + 0])));
-    top2_insert(l1, l2, static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(v[j + 1])));
-    top2_insert(l1, l2, static_cast<int>(static_cast<uint32_t>(cc.z) - 512u * static_cast<uint32_t>(v[j + 2])));
-    top2_insert(l1, l2, static_cast<int>(static_cast<uint32_t>(cc.w) - 512u * static_cast<uint32_t>(v[j + 3])));
+  for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
+  const int m = max(__vimax3_s32(g[0], g[1], g[2]), g[3]);
+#if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
+  l1 = min(l1, m + T + cmin);
+  return;
+#endif
+  DBG_ADD(0, 1);
+#if MVGCUDA_EXPERIMENT == 3
+  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, 2 * m + T >= cmin));  // all lanes vote, lane 0 records
+  DBG_ADD(3, dbg_lane_hits);
+#endif
+  if (__any_sync(0xffffffffu, 2 * m + T >= cmin)) {
+    DBG_ADD(1, 1);
+    // which groups of 4 rows can still matter (all four votes issued back to back)
+    const bool h0 = __any_sync(0xffffffffu, 2 * g[0] + T >= cmin);
+    const bool h1 = __any_sync(0xffffffffu, 2 * g[1] + T >= cmin);
+    const bool h2 = __any_sync(0xffffffffu, 2 * g[2] + T >= cmin);
+    const bool h3 = __any_sync(0xffffffffu, 2 * g[3] + T >= cmin);
+    const bool h[4] = {h0, h1, h2, h3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (h[k]) {
+        DBG_ADD(2, 1);
+        const int4 cc = ptx::lds128(cs_saddr + 16 * k);  // warp-uniform address: smem broadcast
+        const int p0 = static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(x[4 * k + 0]));
+        const int p1 = static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(x[4 * k + 1]));
+        const int p2 = static_cast<int>(static_cast<uint32_t>(cc.z) - 512u * static_cast<uint32_t>(x[4 * k + 2]));
+        const int p3 = static_cast<int>(static_cast<uint32_t>(cc.w) - 512u * static_cast<uint32_t>(x[4 * k + 3]));
+        const Pair2 c = merge2(sort2(p0, p1), sort2(p2, p3));
+        const int nl2 = __vimin3_s32(max(l1, c.lo), l2, c.hi);
+        l1 = min(l1, c.lo);
+        l2 = nl2;
+      }
+    }
+    // 2nd smallest t over {running top-2 of earlier tiles} U {this tile's top-2}
+    T = __vimin3_s32(T, max(g1t, l1 >> 8), l2 >> 8);
+    ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
   }
 }
+
+constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overflow and passes every chunk
+
+// (t, index) lexicographic order: smaller distance first, lower db row on ties
+__device__ __forceinline__ bool cand_less(int ta, int ia, int tb, int ib) { return ta < tb || (ta == tb && ia < ib); }
 
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 B
@@ -133,6 +219,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+#if MVGCUDA_EXPERIMENT == 3
+  if (threadIdx.x < 8) dbg_smem()[threadIdx.x] = 0;
+#endif
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_db);
@@ -167,7 +256,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
           const uint32_t sc = c_it % kSlotsC;
           ptx::mbar_wait(&s.c_empty[sc], ((c_it / kSlotsC) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&s.c_full[sc], kBytesC);
-          ptx::bulk_load_1d(s.c[sc], p.ccol + J.db_row0 + t * kTileDb, kBytesC, &s.c_full[sc]);
+          ptx::bulk_load_1d(s.c[sc], p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, kBytesC, &s.c_full[sc]);
           const uint32_t sb = b_it % kStagesB;
           ptx::mbar_wait(&s.b_empty[sb], ((b_it / kStagesB) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&s.b_full[sb], kBytesB);
@@ -208,63 +297,90 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue: one thread per query row =====================
-    const int quad = warp & 3;  // TMEM lanes 32*quad .. 32*quad+31
+    // ===================== epilogue: kEpiParts threads per query row, each scanning 64 columns of every tile ==========
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. 32*quad+31
+    const int part = (warp - 4) >> 2;     // columns [64*part, 64*part+64) of every tile
+    const int row = quad * 32 + lane;     // query row within the block
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    uint32_t acc_it = 0, c_it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    uint32_t acc_it = 0, c_it = 0, item_it = 0;
+    s.bound[0][row] = kTInit;
+    s.bound[1][row] = kTInit;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_it) {
       int job, qb;
       locate_item(p, item, job, qb);
       const PairJob J = p.jobs[job];
-      const int q_local = qb * kBlockQ + quad * 32 + lane;
+      const int q_local = qb * kBlockQ + row;
       const bool q_ok = q_local < J.q_rows;
       const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
-      // global best two in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
+      // running best two of this thread's columns in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
       int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;
+      const uint32_t bound_saddr = ptx::smem_u32(&s.bound[item_it & 1][row]);
+      // the other parity's slot is idle (every part left the previous item at the barrier below): reset it for the next item
+      s.bound[(item_it & 1) ^ 1][row] = kTInit;
       for (int t = 0; t < ntiles; ++t, ++acc_it, ++c_it) {
         const uint32_t buf = acc_it % kAccBufs;
         const uint32_t sc = c_it % kSlotsC;
         ptx::mbar_wait(&s.c_full[sc], (c_it / kSlotsC) & 1);
         ptx::mbar_wait(&s.acc_full[buf], (acc_it / kAccBufs) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_sel + buf * kTileDb;
-        const int* cs = s.c[sc];
+        const uint32_t taddr = tmem_base + lane_sel + buf * kTileDb + part * kPartCols;
+        const uint32_t cs = ptx::smem_u32(s.c[sc] + part * kPartCols);
         int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;
-        int32_t va[32], vb[32];
-        ptx::tmem_ld_32x32b_x32(taddr, va);
-#pragma unroll
-        for (int c = 0; c < kTileDb / 32; c += 2) {
-          ptx::tmem_ld_wait();
-          ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
-          epi_chunk(va, cs + c * 32, l1, l2);
-          ptx::tmem_ld_wait();
-          if (c + 2 < kTileDb / 32) {
-            ptx::tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
-          } else {
-            // every column of this accumulator is in registers: hand the buffer back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s.acc_empty[buf]);
-          }
-          epi_chunk(vb, cs + (c + 1) * 32, l1, l2);
-        }
+        int T = min(min(g2t, kTInit), ptx::lds32_volatile(bound_saddr));  // admit t <= T
+        const int4 cm = ptx::lds128(ptx::smem_u32(s.c[sc] + kTileDb + part * (kPartCols / kChunk)));
+        const int cmin[4] = {cm.x, cm.y, cm.z, cm.w};
+        int32_t va[16], vb[16];
+        ptx::tmem_ld_32x32b_x16(taddr, va);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x16(taddr + 16, vb);
+        epi_chunk16(va, cs, cmin[0], g1t, bound_saddr, l1, l2, T);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x16(taddr + 32, va);
+        epi_chunk16(vb, cs + 64, cmin[1], g1t, bound_saddr, l1, l2, T);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x16(taddr + 48, vb);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(va, cs + 128, cmin[2], g1t, bound_saddr, l1, l2, T);
+        ptx::tmem_ld_wait();
+        // all of this warp's columns are in registers: hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[buf]);
+        epi_chunk16(vb, cs + 192, cmin[3], g1t, bound_saddr, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index
-        const int base = t * kTileDb;
-        const int t1 = l1 >> 8, i1 = base + (l1 & 255);
-        const int t2 = l2 >> 8, i2 = base + (l2 & 255);
-        if (t1 < g1t) {
-          if (t2 < g1t) { g2t = t2; g2i = i2; } else { g2t = g1t; g2i = g1i; }
-          g1t = t1; g1i = i1;
-        } else if (t1 < g2t) {
-          g2t = t1; g2i = i1;
+        if (l1 != 0x7FFFFFFF) {
+          const int base = t * kTileDb;
+          const int t1 = l1 >> 8, i1 = base + (l1 & 255);
+          const int t2 = l2 >> 8, i2 = base + (l2 & 255);
+          if (t1 < g1t) {
+            if (t2 < g1t) { g2t = t2; g2i = i2; } else { g2t = g1t; g2i = g1i; }
+            g1t = t1; g1i = i1;
+          } else if (t1 < g2t) {
+            g2t = t1; g2i = i1;
+          }
         }
       }
-      if (q_ok) {
-        const int qn = p.ccol[J.q_row0 + q_local] >> 8;
+      // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record
+      if (part > 0) s.xchg[item_it & 1][part - 1][row] = make_int4(g1t, g1i, g2t, g2i);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");  // the warps sharing these 32 queries
+      if (part == 0 && q_ok) {
+        int b1t = g1t, b1i = g1i, b2t = g2t, b2i = g2i;
+#pragma unroll
+        for (int o_ = 0; o_ < kEpiParts - 1; ++o_) {
+          const int4 o = s.xchg[item_it & 1][o_][row];
+          if (cand_less(o.x, o.y, b1t, b1i)) {
+            if (cand_less(o.z, o.w, b1t, b1i)) { b2t = o.z; b2i = o.w; } else { b2t = b1t; b2i = b1i; }
+            b1t = o.x; b1i = o.y;
+          } else if (cand_less(o.x, o.y, b2t, b2i)) {
+            b2t = o.x; b2i = o.y;
+          }
+        }
+        const int qn = p.ccol[ccol_index(J.q_row0 + q_local)] >> 8;
         KnnRecord r;
-        r.idx1 = g1i; r.idx2 = g2i; r.d1 = qn + g1t; r.d2 = qn + g2t;
+        r.idx1 = b1i; r.idx2 = b2i; r.d1 = qn + b1t; r.d2 = qn + b2t;
         *reinterpret_cast<int4*>(&p.out[J.out_off + q_local]) = *reinterpret_cast<const int4*>(&r);
       }
     }
@@ -273,6 +389,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+#if MVGCUDA_EXPERIMENT == 3
+  if (threadIdx.x < 8) atomicAdd(&g_dbg[threadIdx.x], (unsigned long long)dbg_smem()[threadIdx.x]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ probe

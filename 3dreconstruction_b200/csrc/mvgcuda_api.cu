@@ -193,7 +193,7 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   A.row0[n_images] = (int)total;
   A.arena_rows = (int)std::max<long long>(total, kRowAlign);
   CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
-  CU_CHECK(ctx, A.ccol.reserve(A.arena_rows));
+  CU_CHECK(ctx, A.ccol.reserve((size_t)(A.arena_rows / kTileDb) * kTileC));
   CU_CHECK(ctx, A.img_row0.reserve(n_images + 1));
   CU_CHECK(ctx, A.img_rows.reserve(std::max(n_images, 1)));
   cudaStream_t st = ctx->stream;
@@ -207,9 +207,8 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   if (n_images)
     CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
-  const long long threads = (long long)A.arena_rows * 8;
-  row_consts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A.desc.p, A.img_row0.p, A.img_rows.p, n_images,
-                                                                      A.arena_rows, A.ccol.p);
+  row_consts_kernel<<<A.arena_rows / 32, 256, 0, st>>>(A.desc.p, A.img_row0.p, A.img_rows.p, n_images, A.arena_rows,
+                                                       A.ccol.p);
   CU_CHECK(ctx, cudaGetLastError());
   int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
   if (rc) return rc;
@@ -710,5 +709,15 @@ int mvgcuda_probe_i8_peak(mvgcuda_ctx* ctx, int iters, double* ops_per_sec, floa
   if (ops_per_sec) *ops_per_sec = 2.0 * kBlockQ * kTileDb * 32.0 * (double)iters * grid / (ms * 1e-3);
   return MVGCUDA_OK;
 }
+
+#if MVGCUDA_EXPERIMENT == 3
+// developer probe builds only (not part of include/mvgcuda.h)
+int mvgcuda_debug_counters(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof z); }
+  return 0;
+}
+#endif
 
 }  // extern "C"

@@ -30,35 +30,68 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint
+// (nanoseconds) expires, so a waiting role does not burn issue slots of the SM sub-partition it shares with
+// the epilogue warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
 
-// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never
-// as a hung GPU box.  ~4e9 SM cycles is seconds, far beyond any legitimate wait here.
-#ifndef MVGCUDA_WAIT_LIMIT_CYCLES
-#define MVGCUDA_WAIT_LIMIT_CYCLES 4000000000ll
-#endif
+// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU
+// box.  The wall clock is consulted every 64 failed polls; 2 s is far beyond any legitimate wait here.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > MVGCUDA_WAIT_LIMIT_CYCLES) {
-      printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++polls & 63u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) {
+        printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
+}
+
+// Explicit shared-space loads (a generic pointer into shared memory makes the compiler emit generic LD).
+__device__ __forceinline__ int4 lds128(uint32_t saddr) {
+  int4 r;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ int lds32(uint32_t saddr) {
+  int r;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ int lds32_volatile(uint32_t saddr) {
+  int r;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void red_min_shared(uint32_t saddr, int v) {
+  asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -148,6 +181,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int32_t (&v)[
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }

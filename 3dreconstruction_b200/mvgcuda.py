@@ -24,7 +24,7 @@ TIE_LOWEST_INDEX = 0
 TIE_REFERENCE = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvgcuda.so")
+LIB_PATH = os.environ.get("MVGCUDA_LIB", os.path.join(_HERE, "libmvgcuda.so"))  # override: developer probes
 
 
 class MvgCudaError(RuntimeError):
