@@ -1,0 +1,105 @@
+// test_adaptors.cpp -- the C++ drop-in adaptors (include/mvgcuda/*.h) against the REFERENCE'S OWN classes, in one
+// binary: ArrayMatcherCuda vs ArrayMatcherBruteForce, MatcherCudaAllInMemory vs MatcherAllInMemory.
+// Built by tests/native/build_native.sh where the reference tree is mounted (it needs the reference headers); the
+// binary travels to the GPU box.  Usage: test_adaptors <match_dir> <name1> <name2> ...   (names of images whose
+// .feat/.desc live in match_dir).  Exit code 0 and "ADAPTORS OK" on success.
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "mvg/utils/progress.h"
+using namespace std;
+using namespace mvg::utils;
+
+#include "mvg/feature/features.h"
+#include "mvg/feature/indexed_match_utils.h"
+#include "mvg/feature/matcher_all_in_memory.h"
+#include "mvg/feature/matcher_brute_force.h"
+#include "mvgcuda/array_matcher_cuda.h"
+#include "mvgcuda/matcher_cuda_all_in_memory.h"
+
+using namespace mvg::feature;
+typedef Descriptor<unsigned char, 128> DescriptorT;
+typedef ScalePointFeature FeatureT;
+typedef KeypointSet<std::vector<FeatureT>, std::vector<DescriptorT> > KeypointSetT;
+typedef SquaredEuclideanDistanceVectorized<unsigned char> MetricT;
+typedef ArrayMatcherBruteForce<unsigned char, MetricT> MatcherBF;
+
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { std::cerr << "CHECK failed: " #c " (line " << __LINE__ << ")" << std::endl; ++fails; } } while (0)
+
+static std::vector<unsigned char> rnd(int rows, int alphabet, unsigned seed) {
+  std::mt19937 g(seed);
+  std::vector<unsigned char> v((size_t)rows * 128);
+  for (auto& b : v) b = (unsigned char)(g() % alphabet);
+  return v;
+}
+
+static void array_level(int db_rows, int nq, int alphabet, unsigned seed) {
+  std::vector<unsigned char> db = rnd(db_rows, alphabet, seed), q = rnd(nq, alphabet, seed + 1);
+  MatcherBF ref;
+  ArrayMatcherCuda<unsigned char, MetricT> gpu;
+  ArrayMatcher<unsigned char, MetricT>* base = &gpu;   // used through the reference's abstract interface
+  CHECK(ref.Build(db.data(), db_rows, 128) == base->Build(db.data(), db_rows, 128));
+  std::vector<int> i0(1, 42), i1(1, 42);
+  std::vector<float> d0(1, 7.f), d1(1, 7.f);   // pre-filled: both APPEND
+  const bool r0 = ref.SearchNeighbours(q.data(), nq, &i0, &d0, 2);
+  const bool r1 = base->SearchNeighbours(q.data(), nq, &i1, &d1, 2);
+  CHECK(r0 == r1);
+  CHECK(i0 == i1);
+  CHECK(d0 == d1);
+  if (i0 != i1) std::cerr << "  array_level(" << db_rows << "," << nq << "," << alphabet << ") indices differ" << std::endl;
+}
+
+int main(int argc, char** argv) {
+  // array level: random, tie-heavy, degenerate
+  array_level(300, 200, 256, 1);
+  array_level(1000, 513, 3, 2);
+  array_level(2, 5, 2, 3);
+  array_level(1, 4, 256, 4);   // k=2 > rows: both return false, outputs untouched
+  {
+    ArrayMatcherCuda<unsigned char, MetricT> gpu;
+    CHECK(!gpu.Build(NULL, 0, 128));
+    std::vector<unsigned char> db = rnd(50, 256, 9), q = rnd(1, 256, 10);
+    CHECK(gpu.Build(db.data(), 50, 128));
+    int idx = -1; float dist = -1.f;
+    CHECK(gpu.SearchNeighbour(q.data(), &idx, &dist));
+    MetricT m; float best = 1e30f; int bi = -1;
+    for (int r = 0; r < 50; ++r) { float d = m(q.data(), db.data() + r * 128, 128); if (d < best) { best = d; bi = r; } }
+    CHECK(idx == bi && dist == best);
+  }
+  // collection level on files
+  if (argc >= 4) {
+    const std::string dir = argv[1];
+    std::vector<std::string> names;
+    for (int k = 2; k < argc; ++k) names.push_back(argv[k]);
+    for (float ratio : {0.6f, 0.8f}) {
+      MatcherAllInMemory<KeypointSetT, MatcherBF> ref(ratio);
+      MatcherCudaAllInMemory<KeypointSetT> gpu(ratio, 1);
+      CHECK(ref.LoadData(names, dir));
+      CHECK(gpu.LoadData(names, dir));
+      PairWiseMatches m0, m1;
+      std::streambuf* old = std::cout.rdbuf();
+      std::ostringstream sink;
+      std::cout.rdbuf(sink.rdbuf());
+      ref.Match(names, m0);
+      std::cout.rdbuf(old);
+      const Matcher& as_base = gpu;   // through the reference's abstract Matcher interface
+      as_base.Match(names, m1);
+      std::ostringstream s0, s1;
+      PairedIndexedMatchToStream(m0, s0);
+      PairedIndexedMatchToStream(m1, s1);
+      CHECK(m0.size() == m1.size());
+      CHECK(s0.str() == s1.str());
+      std::cout << "collection ratio " << ratio << ": " << m0.size() << " pairs, " << s0.str().size() << " bytes, identical="
+                << (s0.str() == s1.str()) << std::endl;
+    }
+  }
+  std::cout << (fails ? "ADAPTORS FAILED" : "ADAPTORS OK") << std::endl;
+  return fails ? 1 : 0;
+}

@@ -1,0 +1,43 @@
+"""The C++ host side on a GPU: the compute_matches driver (flags/files as the reference's CLI) and the header-only
+adaptors compiled against the REFERENCE'S OWN headers (binary built where /root/reference is mounted)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "build", "compute_matches")
+ADAPT = os.path.join(ROOT, "build", "native", "test_adaptors")
+
+
+def _write_et(pkg, et, d, hdr=8):
+    descs, feats = et
+    names = []
+    for k, (dd, ff) in enumerate(zip(descs, feats)):
+        names.append(f"et{k:03d}.jpg")
+        pkg.io.save_descs_bin(str(d / f"et{k:03d}.desc"), dd, hdr)
+        pkg.io.save_feats(str(d / f"et{k:03d}.feat"), ff)
+    (d / "lists.txt").write_text("".join(f"{n};640;480;649.156;Canon;Canon PowerShot A10\n" for n in names))
+    return names
+
+
+@pytest.mark.parametrize("r,hdr", [("0.6", 4), ("0.8", 8)])
+def test_compute_matches_driver_golden(pkg, et, tmp_path, r, hdr):
+    _write_et(pkg, et, tmp_path, hdr)
+    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", r, "--gpus", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    got = (tmp_path / "matches.putative.txt").read_bytes()
+    assert got == open(os.path.join(GOLDEN, f"et_putative_r{r}.txt"), "rb").read()
+    # second invocation takes the resume short-cut
+    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", r], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "PREVIOUS RESULTS LOADED" in out.stdout
+
+
+def test_adaptors_against_reference_classes(pkg, et, tmp_path):
+    if not os.path.exists(ADAPT):
+        pytest.skip("build/native/test_adaptors not built (needs the reference headers at build time)")
+    names = _write_et(pkg, et, tmp_path, 8)
+    out = subprocess.run([ADAPT, str(tmp_path), *names], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ADAPTORS OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
