@@ -44,7 +44,8 @@ constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
 constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant: they share 32 queries and split each tile's columns
 constexpr int kNumEpiWarps = 4 * kEpiParts;
 constexpr int kPartCols = kTileDb / kEpiParts;        // 64 columns of every tile per warp
-constexpr int kKnnThreads = 128 + 32 * kNumEpiWarps;  // warps 0..3: TMA, MMA, TMEM-alloc, spare; 4.. epilogue
+constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer
+constexpr int kKnnThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);  // 576 threads -> 112 registers per thread
 
 struct PairJob {
   int db_row0;  // arena row of image I (db), multiple of kRowAlign
@@ -233,7 +234,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&s.acc_full[i], 1); ptx::mbar_init(&s.acc_empty[i], kNumEpiWarps); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<512>(&s.tmem_base);
+  if (warp == 0) ptx::tmem_alloc<512>(&s.tmem_base);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -296,10 +297,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else {
     // ===================== epilogue: kEpiParts threads per query row, each scanning 64 columns of every tile ==========
-    const int quad = warp & 3;            // TMEM lanes 32*quad .. 32*quad+31
-    const int part = (warp - 4) >> 2;     // columns [64*part, 64*part+64) of every tile
+    const int quad = warp & 3;            // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
+    const int part = (warp - kFirstEpiWarp) >> 2;  // columns [64*part, 64*part+64) of every tile
     const int row = quad * 32 + lane;     // query row within the block
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t acc_it = 0, c_it = 0, item_it = 0;
@@ -330,24 +331,22 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         int T = min(min(g2t, kTInit), ptx::lds32_volatile(bound_saddr));  // admit t <= T
         const int4 cm = ptx::lds128(ptx::smem_u32(s.c[sc] + kTileDb + part * (kPartCols / kChunk)));
         const int cmin[4] = {cm.x, cm.y, cm.z, cm.w};
-        int32_t va[16], vb[16];
-        ptx::tmem_ld_32x32b_x16(taddr, va);
+        // drain this warp's 64 columns into registers and hand the accumulator straight back to the MMA warp: the
+        // TMEM buffer is then held for one load latency, not for the (data-dependent) time the filter takes
+        int32_t v0[16], v1[16], v2[16], v3[16];
+        ptx::tmem_ld_32x32b_x16(taddr, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
         ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 16, vb);
-        epi_chunk16(va, cs, cmin[0], g1t, bound_saddr, l1, l2, T);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 32, va);
-        epi_chunk16(vb, cs + 64, cmin[1], g1t, bound_saddr, l1, l2, T);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 48, vb);
-        T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(va, cs + 128, cmin[2], g1t, bound_saddr, l1, l2, T);
-        ptx::tmem_ld_wait();
-        // all of this warp's columns are in registers: hand the accumulator back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.acc_empty[buf]);
-        epi_chunk16(vb, cs + 192, cmin[3], g1t, bound_saddr, l1, l2, T);
+        epi_chunk16(v0, cs, cmin[0], g1t, bound_saddr, l1, l2, T);
+        epi_chunk16(v1, cs + 64, cmin[1], g1t, bound_saddr, l1, l2, T);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v2, cs + 128, cmin[2], g1t, bound_saddr, l1, l2, T);
+        epi_chunk16(v3, cs + 192, cmin[3], g1t, bound_saddr, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index
@@ -388,7 +387,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
 #if MVGCUDA_EXPERIMENT == 3
   if (threadIdx.x < 8) atomicAdd(&g_dbg[threadIdx.x], (unsigned long long)dbg_smem()[threadIdx.x]);
 #endif
