@@ -284,6 +284,12 @@ def run_ours(args):
         cpu = cpu_reference_run(nq=nq)
         cpu.pop("seconds", None)
         cpu.pop("pairs_equiv", None)
+        try:  # the reference's shipped default matcher (FLANN kd-tree, approximate + randomised): speed only
+            fl = cpu_reference_run(nq=ROWS, flann=True)
+            cpu["flann_kdtree"] = {"value": fl["value"], "unit": "pairs/s", "cores": fl["cores"], "sample": fl["sample"],
+                                   "note": "ArrayMatcherKdtreeFlann<uchar, flann::L2<uchar>>, 4 trees / 128 checks (matcher_kdtree_flann.h:47-49,115); results are approximate"}
+        except Exception as e:  # FLANN not compiled into oracle/_ref
+            cpu["flann_kdtree"] = {"unavailable": str(e)}
 
     if rank == 0:
         line = {

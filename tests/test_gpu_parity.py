@@ -265,3 +265,45 @@ def test_self_match_and_permutation_properties(ctx, pkg):
     assert np.array_equal(d1, d2)
     uniq = d1[:, 0] < d1[:, 1]
     assert np.array_equal(perm[i2[uniq, 0]], i1[uniq, 0])
+
+
+@pytest.mark.parametrize("name", ["sceaux", "ace"])
+@pytest.mark.parametrize("r", [0.6, 0.8])
+def test_collection_golden_imagedata(ctx, pkg, name, r, tmp_path):
+    """BASELINE configs[0]: bundled data/imageData image pairs (real RootSIFT u8 regions from the reference's own VLFeat
+    wrapper), putative file byte-identical to the reference's brute-force run."""
+    z = np.load(os.path.join(GOLDEN, "imagedata_collection.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "imagedata_golden.json")))[name]
+    descs = [z[f"{name}_desc_{k}"] for k in range(2)]
+    feats = [z[f"{name}_feat_{k}"][:, :2] for k in range(2)]
+    m = pkg.MatcherCudaAllInMemory(r, ctx)
+    m.LoadArrays(descs, feats)
+    pw = m.Match()
+    assert sum(len(v) for v in pw.values()) == meta[f"r{r}"]["matches"]
+    out = str(tmp_path / "m.txt")
+    m.Export(out)
+    data = open(out, "rb").read()
+    assert data == z[f"{name}_text_r{r}"].tobytes() and hashlib.sha256(data).hexdigest() == meta[f"r{r}"]["sha256"]
+
+
+def test_config4_shape_8k_rows(ctx, pkg, l1):
+    """configs[3] shape (8,000 rows per image): a 6-image slice, every pair bit-exact vs the oracle."""
+    descs = synth.collection(4, 6, 8000)
+    ctx.upload_images(descs)
+    pairs = pkg.pairs_exhaustive(6)
+    rs = float(pkg.square_f32(0.8))
+    res = ctx.match_pairs(pairs, rs)
+    for p, (i, j) in enumerate(pairs):
+        assert np.array_equal(res.pair(p), l1.pair_matches(descs[i], descs[j], rs)), (i, j)
+
+
+def test_ragged_collection_many_sizes(ctx, pkg, l1):
+    """Ragged images (sizes straddling every tile / block / chunk boundary) in one batch."""
+    sizes = [2, 3, 15, 16, 17, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513, 1025]
+    descs = [synth.tie_set(900 + k, n, 4) if k % 2 else synth.uniform_set(900 + k, n) for k, n in enumerate(sizes)]
+    ctx.upload_images(descs)
+    pairs = pkg.pairs_exhaustive(len(sizes))
+    rs = float(pkg.square_f32(0.8))
+    res = ctx.match_pairs(pairs, rs)
+    for p, (i, j) in enumerate(pairs):
+        assert np.array_equal(res.pair(p), l1.pair_matches(descs[i], descs[j], rs)), (sizes[i], sizes[j])

@@ -201,3 +201,20 @@ def test_edge_cases(l1):
     q2 = np.zeros((3, 128), np.uint8); q2[1] = 1; q2[2] = 199
     m = l1.pair_matches(db, q2, 0.64)                      # three pass -> last dropped
     assert m.tolist() == [[0, 0]] or m.tolist() == [[0, 0], [0, 1]][:1]
+
+
+@pytest.mark.parametrize("name", ["sceaux", "ace"])
+@pytest.mark.parametrize("r", [0.6, 0.8])
+def test_l1_collection_golden_imagedata(l1, pkg, name, r, tmp_path):
+    """BASELINE configs[0]: the reference's bundled data/imageData pairs, SIFT regions from the reference's own wrapper,
+    reference BF matcher output (tests/golden/make_golden_imagedata.py)."""
+    z = np.load(os.path.join(GOLDEN, "imagedata_collection.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "imagedata_golden.json")))[name]
+    descs = [z[f"{name}_desc_{k}"] for k in range(2)]
+    feats = [z[f"{name}_feat_{k}"][:, :2] for k in range(2)]
+    assert [len(d) for d in descs] == meta["rows"]
+    pw = l1.match_collection(descs, feats, pkg.pairs_exhaustive(2), float(pkg.square_f32(r)))
+    out = tmp_path / "m.txt"
+    l1.export_text(pw, str(out))
+    assert out.read_bytes() == z[f"{name}_text_r{r}"].tobytes()
+    assert sum(len(v) for v in pw.values()) == meta[f"r{r}"]["matches"]
