@@ -41,9 +41,9 @@ constexpr int kChunk = 16;                     // db rows per filter decision in
 constexpr int kTileC = kTileDb + kTileDb / kChunk;  // per-tile constants: 256 packed (norm<<8|col) + 16 chunk-min norms
 constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
 
-constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant: they share 32 queries and split each tile's columns
+constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant; they share 32 queries: 2 column halves x 2 tile parities
 constexpr int kNumEpiWarps = 4 * kEpiParts;
-constexpr int kPartCols = kTileDb / kEpiParts;        // 64 columns of every tile per warp
+constexpr int kPartCols = kTileDb / 2;                // 128 columns of every other tile per warp
 constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer
 constexpr int kKnnThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);  // 576 threads -> 112 registers per thread
 
@@ -81,6 +81,7 @@ struct KnnParams {
   int n_jobs;
   int n_items;
   KnnRecord* __restrict__ out;
+  int two;  // always 2; a run-time value so that 2*x+T stays an IMAD (idle FMA pipe) instead of an IADD3 (ALU pipe, the bottleneck)
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -159,7 +160,8 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
 // Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
 // by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
 __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
-                                            const int g1t, const uint32_t bound_saddr, int& l1, int& l2, int& T) {
+                                            const int g1t, const uint32_t bound_saddr, const int two, int& l1, int& l2,
+                                            int& T) {
 #if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
   l1 = min(l1, x[0]);
   return;
@@ -174,16 +176,16 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
 #endif
   DBG_ADD(0, 1);
 #if MVGCUDA_EXPERIMENT == 3
-  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, 2 * m + T >= cmin));  // all lanes vote, lane 0 records
+  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, two * m + T >= cmin));  // all lanes vote, lane 0 records
   DBG_ADD(3, dbg_lane_hits);
 #endif
-  if (__any_sync(0xffffffffu, 2 * m + T >= cmin)) {
+  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
     DBG_ADD(1, 1);
     // which groups of 4 rows can still matter (all four votes issued back to back)
-    const bool h0 = __any_sync(0xffffffffu, 2 * g[0] + T >= cmin);
-    const bool h1 = __any_sync(0xffffffffu, 2 * g[1] + T >= cmin);
-    const bool h2 = __any_sync(0xffffffffu, 2 * g[2] + T >= cmin);
-    const bool h3 = __any_sync(0xffffffffu, 2 * g[3] + T >= cmin);
+    const bool h0 = __any_sync(0xffffffffu, two * g[0] + T >= cmin);
+    const bool h1 = __any_sync(0xffffffffu, two * g[1] + T >= cmin);
+    const bool h2 = __any_sync(0xffffffffu, two * g[2] + T >= cmin);
+    const bool h3 = __any_sync(0xffffffffu, two * g[3] + T >= cmin);
     const bool h[4] = {h0, h1, h2, h3};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -230,8 +232,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(&s.a_full[i], 1); ptx::mbar_init(&s.a_empty[i], 1); }
     for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(&s.b_full[i], 1); ptx::mbar_init(&s.b_empty[i], 1); }
-    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kNumEpiWarps); }
-    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&s.acc_full[i], 1); ptx::mbar_init(&s.acc_empty[i], kNumEpiWarps); }
+    // a tile is consumed by the 8 epilogue warps of one tile-parity group
+    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kNumEpiWarps / 2); }
+    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&s.acc_full[i], 1); ptx::mbar_init(&s.acc_empty[i], kNumEpiWarps / 2); }
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc<512>(&s.tmem_base);
@@ -298,11 +301,17 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: kEpiParts threads per query row, each scanning 64 columns of every tile ==========
-    const int quad = warp & 3;            // TMEM lanes 32*quad .. 32*quad+31 (a warp may only touch its own quadrant)
-    const int part = (warp - kFirstEpiWarp) >> 2;  // columns [64*part, 64*part+64) of every tile
+    // ===================== epilogue: kEpiParts threads per query row =====================
+    // Warp (quad, half, par) owns TMEM lanes 32*quad.., columns [128*half, 128*half+128) of the tiles whose running
+    // accumulator index has parity `par` (those tiles always land in TMEM buffer `par`).  Two parities x two halves:
+    // per-tile fixed costs are paid once per 128 columns, and the two parity groups drift independently.
+    const int quad = warp & 3;            // a warp may only touch its own TMEM lane quadrant
+    const int part = (warp - kFirstEpiWarp) >> 2;
+    const int half = part & 1;
+    const uint32_t par = static_cast<uint32_t>(part >> 1);
     const int row = quad * 32 + lane;     // query row within the block
-    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const int two = p.two;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + par * kTileDb + half * kPartCols;
     uint32_t acc_it = 0, c_it = 0, item_it = 0;
     s.bound[0][row] = kTInit;
     s.bound[1][row] = kTInit;
@@ -320,33 +329,44 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       // the other parity's slot is idle (every part left the previous item at the barrier below): reset it for the next item
       s.bound[(item_it & 1) ^ 1][row] = kTInit;
       for (int t = 0; t < ntiles; ++t, ++acc_it, ++c_it) {
-        const uint32_t buf = acc_it % kAccBufs;
+        if ((acc_it & 1u) != par) continue;  // the other group's tile
         const uint32_t sc = c_it % kSlotsC;
         ptx::mbar_wait(&s.c_full[sc], (c_it / kSlotsC) & 1);
-        ptx::mbar_wait(&s.acc_full[buf], (acc_it / kAccBufs) & 1);
+        ptx::mbar_wait(&s.acc_full[par], (acc_it >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_sel + buf * kTileDb + part * kPartCols;
-        const uint32_t cs = ptx::smem_u32(s.c[sc] + part * kPartCols);
+        const uint32_t cs = ptx::smem_u32(s.c[sc] + half * kPartCols);
         int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;
         int T = min(min(g2t, kTInit), ptx::lds32_volatile(bound_saddr));  // admit t <= T
-        const int4 cm = ptx::lds128(ptx::smem_u32(s.c[sc] + kTileDb + part * (kPartCols / kChunk)));
-        const int cmin[4] = {cm.x, cm.y, cm.z, cm.w};
-        // drain this warp's 64 columns into registers and hand the accumulator straight back to the MMA warp: the
-        // TMEM buffer is then held for one load latency, not for the (data-dependent) time the filter takes
+        const uint32_t cm_saddr = ptx::smem_u32(s.c[sc] + kTileDb + half * (kPartCols / kChunk));
+        const int4 cm0 = ptx::lds128(cm_saddr);
+        const int4 cm1 = ptx::lds128(cm_saddr + 16);
         int32_t v0[16], v1[16], v2[16], v3[16];
+        // first 64 columns
         ptx::tmem_ld_32x32b_x16(taddr, v0);
         ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
         ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
         ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
         ptx::tmem_ld_wait();
+        epi_chunk16(v0, cs, cm0.x, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 64, cm0.y, g1t, bound_saddr, two, l1, l2, T);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v2, cs + 128, cm0.z, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 192, cm0.w, g1t, bound_saddr, two, l1, l2, T);
+        // second 64 columns; once they are in registers the accumulator goes back to the MMA warp
+        ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 96, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 112, v3);
+        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[buf]);
-        epi_chunk16(v0, cs, cmin[0], g1t, bound_saddr, l1, l2, T);
-        epi_chunk16(v1, cs + 64, cmin[1], g1t, bound_saddr, l1, l2, T);
+        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 128, cmin[2], g1t, bound_saddr, l1, l2, T);
-        epi_chunk16(v3, cs + 192, cmin[3], g1t, bound_saddr, l1, l2, T);
+        epi_chunk16(v0, cs + 256, cm1.x, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 320, cm1.y, g1t, bound_saddr, two, l1, l2, T);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v2, cs + 384, cm1.z, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 448, cm1.w, g1t, bound_saddr, two, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index

@@ -256,6 +256,7 @@ static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp) {
   kp.n_jobs = bp.n_jobs;
   kp.n_items = bp.n_items;
   kp.out = ctx->d_knn.p;
+  kp.two = 2;
   const int grid = std::min(bp.n_items, ctx->prop.multiProcessorCount);
   knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(A.tmap_q, A.tmap_db, kp);
   CU_CHECK(ctx, cudaGetLastError());
