@@ -10,6 +10,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <shared_mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -289,8 +294,17 @@ static int validate_pairs(mvgcuda_ctx* ctx, const Arena& A, int64_t n_pairs, con
   return MVGCUDA_OK;
 }
 
+// Optional consumer of finished batches (collection level): `on_batch(p1)` is called as soon as the raw matches of
+// pairs [0, p1) are on the host, so that the host-side coordinate de-dup overlaps the GPU work of the next batch.
+// `results_mtx` is held exclusively while the pinned result buffer is re-allocated.
+struct BatchSink {
+  std::function<void(int64_t)> on_batch;
+  std::shared_mutex* results_mtx = nullptr;
+  long long batch_records = 0;  // smaller batches than the default, for a finer pipeline
+};
+
 static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,
-                            mvgcuda_pair_matches* out) {
+                            mvgcuda_pair_matches* out, BatchSink* sink = nullptr) {
   const Arena& A = ctx->images;
   int rc = validate_pairs(ctx, A, n_pairs, pairs);
   if (rc) return rc;
@@ -312,7 +326,7 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     long long rec = 0;
     while (p1 < n_pairs && (p1 - p0) < kBatchPairs) {
       const long long qr = A.rows[pairs[2 * p1 + 1]];
-      if (p1 > p0 && rec + qr > kBatchRecords) break;
+      if (p1 > p0 && rec + qr > (sink && sink->batch_records ? sink->batch_records : kBatchRecords)) break;
       rec += qr;
       ++p1;
     }
@@ -346,7 +360,12 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     CU_CHECK(ctx, cudaStreamSynchronize(st));
     const long long new_total = ctx->h_total.p[0];
     const long long nm = new_total - match_base;
-    CU_CHECK(ctx, ctx->r_matches.reserve((size_t)std::max<long long>(new_total, 1) * 2, (size_t)match_base * 2));
+    {
+      std::unique_lock<std::shared_mutex> lk;
+      if (sink && sink->results_mtx && (size_t)std::max<long long>(new_total, 1) * 2 > ctx->r_matches.cap)
+        lk = std::unique_lock<std::shared_mutex>(*sink->results_mtx);  // readers of the old buffer finish first
+      CU_CHECK(ctx, ctx->r_matches.reserve((size_t)std::max<long long>(new_total, 1) * 2, (size_t)match_base * 2));
+    }
     if (nm > 0) {
       CU_CHECK(ctx, cudaMemcpyAsync(ctx->r_matches.p + match_base * 2, ctx->d_matches.p, nm * sizeof(int2),
                                     cudaMemcpyDeviceToHost, st));
@@ -364,6 +383,7 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     launches += 3;
     match_base = new_total;
     p0 = p1;
+    if (sink && sink->on_batch) sink->on_batch(p1);
   }
   ctx->r_offsets.p[n_pairs] = match_base;
   if (out) {
@@ -592,30 +612,50 @@ int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* p
                              int host_threads, mvgcuda_pair_matches* out) {
   if (!ctx) return MVGCUDA_ERR_INVALID;
   if (ctx->feats.size() != ctx->images.rows.size()) { ctx->set_error("match_collection: call mvgcuda_set_features first"); return MVGCUDA_ERR_INVALID; }
-  mvgcuda_pair_matches raw;
-  int rc = match_pairs_impl(ctx, n_pairs, pairs, ratio_sq, &raw);
-  if (rc) return rc;
   if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
   host_threads = (int)std::min<int64_t>(host_threads, std::max<int64_t>(n_pairs, 1));
+  // Host pool: pair p is de-duplicated as soon as its batch has landed, while the GPU works on the next batch.
   std::vector<std::vector<int>> per_pair(n_pairs);
-  std::atomic<int64_t> cursor{0};
+  std::atomic<int64_t> cursor{0}, avail{0};
+  std::atomic<bool> failed{false};
+  std::mutex cv_m;
+  std::condition_variable cv;
+  std::shared_mutex results_mtx;
   auto work = [&]() {
     std::vector<int> tmp;
     for (;;) {
       const int64_t p = cursor.fetch_add(1);
       if (p >= n_pairs) break;
+      if (avail.load(std::memory_order_acquire) <= p) {
+        std::unique_lock<std::mutex> lk(cv_m);
+        cv.wait(lk, [&] { return avail.load(std::memory_order_acquire) > p || failed.load(); });
+      }
+      if (failed.load()) break;
       const int I = pairs[2 * p], J = pairs[2 * p + 1];
-      dedup_xy(ctx->feats[I].data(), ctx->feats[J].data(), raw.matches + 2 * raw.offsets[p], raw.counts[p], tmp);
+      {
+        std::shared_lock<std::shared_mutex> lk(results_mtx);
+        dedup_xy(ctx->feats[I].data(), ctx->feats[J].data(), ctx->r_matches.p + 2 * ctx->r_offsets.p[p], ctx->r_counts.p[p], tmp);
+      }
       per_pair[p] = tmp;
     }
   };
-  if (host_threads == 1) {
-    work();
-  } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < host_threads; ++t) th.emplace_back(work);
-    for (auto& t : th) t.join();
+  std::vector<std::thread> th;
+  for (int t = 0; t < host_threads; ++t) th.emplace_back(work);
+  BatchSink sink;
+  sink.results_mtx = &results_mtx;
+  sink.batch_records = 6ll << 20;
+  sink.on_batch = [&](int64_t p1) {
+    { std::lock_guard<std::mutex> lk(cv_m); avail.store(p1, std::memory_order_release); }
+    cv.notify_all();
+  };
+  mvgcuda_pair_matches raw;
+  int rc = match_pairs_impl(ctx, n_pairs, pairs, ratio_sq, &raw, &sink);
+  if (rc) {
+    { std::lock_guard<std::mutex> lk(cv_m); failed.store(true); }
+    cv.notify_all();
   }
+  for (auto& t : th) t.join();
+  if (rc) return rc;
   ctx->c_counts.resize(n_pairs);
   ctx->c_offsets.resize(n_pairs + 1);
   long long tot = 0;
