@@ -10,8 +10,6 @@
 // All arithmetic on the path is exact int32; the only fp32 operation is the ratio test
 // float(d1) < ratio_sq * float(d2) (one __fmul_rn, strict <), as in the reference.
 #pragma once
-#include <cstdio>
-
 #include "ptx.cuh"
 
 #ifndef MVGCUDA_EXPERIMENT
@@ -30,9 +28,9 @@ namespace mvgcuda {
 constexpr int kDim = 128;      // descriptor bytes == GEMM K
 constexpr int kBlockQ = 128;   // query rows per block   (MMA M, one TMEM lane per query)
 constexpr int kTileDb = 256;   // db rows per tile       (MMA N, one TMEM column per db row)
-constexpr int kStagesB = 3;    // db tile ring (TMA -> MMA)
+constexpr int kStagesB = 4;    // db tile ring (TMA -> MMA)
 constexpr int kSlotsA = 2;     // query block double buffer
-constexpr int kSlotsC = 6;     // per-column constant ring (TMA -> epilogue), outlives the B stage
+constexpr int kSlotsC = 8;     // per-column constant ring (TMA -> epilogue), outlives the B stage
 constexpr int kAccBufs = 2;    // TMEM accumulator double buffer (2 x 256 columns = all 512)
 constexpr int kRowAlign = 256; // every image starts at a multiple of this in the arena
 constexpr int kPadNorm = 0x7FFFFF;  // "norm" of padding rows: > 128*255^2, so they never win
@@ -40,16 +38,12 @@ constexpr int kPadNorm = 0x7FFFFF;  // "norm" of padding rows: > 128*255^2, so t
 constexpr uint32_t kBytesA = kBlockQ * kDim;        // 16 KB
 constexpr uint32_t kBytesB = kTileDb * kDim;        // 32 KB
 constexpr int kChunk = 16;                     // db rows per filter decision in the epilogue
-// per-tile constants: 256 packed (norm<<8|col) + 16 chunk-min norms + 16 chunk-max norms (real rows only)
-constexpr int kTileC = kTileDb + 2 * (kTileDb / kChunk);
-constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1152 B
-constexpr int kQueueCap = 56;     // candidate-stack entries per epilogue warp (<= kFlushAt-1 before a push of <= 32)
-constexpr int kFlushAt = 24;      // evaluate the top 32 (or all) entries once this many are stacked
-constexpr int kEntryInts = 20;    // 16 raw dot products + 1 meta word, padded to 80 B (conflict-free 128-bit accesses)
+constexpr int kTileC = kTileDb + kTileDb / kChunk;  // per-tile constants: 256 packed (norm<<8|col) + 16 chunk-min norms
+constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
 
-constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant; they share 32 queries and split each tile's columns
+constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant; they share 32 queries: 2 column halves x 2 tile parities
 constexpr int kNumEpiWarps = 4 * kEpiParts;
-constexpr int kPartCols = kTileDb / kEpiParts;        // 64 columns of every tile per warp
+constexpr int kPartCols = kTileDb / 2;                // 128 columns of every other tile per warp
 constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer
 constexpr int kKnnThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);  // 576 threads -> 112 registers per thread
 
@@ -77,11 +71,7 @@ struct KnnSmem {
   uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
   uint32_t tmem_base;
   int bound[2][kBlockQ];  // per (item parity, query): best-known 2nd-smallest t, atomically tightened by all parts
-  // exact running top-2 per (item parity, query) as 64-bit keys (t biased to unsigned << 32 | db row): smaller = nearer,
-  // lower row on ties; updated lock-free with 64-bit atomic min by whichever lane evaluates a candidate of that query
-  alignas(8) unsigned long long best[2][kBlockQ];
-  alignas(8) unsigned long long second[2][kBlockQ];
-  alignas(16) int queue[kNumEpiWarps][kQueueCap][kEntryInts];  // per-warp stack of (lane, chunk) candidates
+  alignas(16) int4 xchg[2][kEpiParts - 1][kBlockQ];  // parts 1.. hand their top-2 to part 0 at the end of an item
 };
 
 struct KnnParams {
@@ -128,17 +118,11 @@ row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img
   }
   __syncthreads();
   if (threadIdx.x < 2) {
-    int mn = kPadNorm, mx = -1;
+    int m = norms[threadIdx.x * 16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int v = norms[threadIdx.x * 16 + k];
-      mn = min(mn, v);
-      if (v != kPadNorm) mx = max(mx, v);  // padding rows do not count
-    }
-    if (mx < 0) mx = kPadNorm;  // a chunk of padding only
+    for (int k = 1; k < 16; ++k) m = min(m, norms[threadIdx.x * 16 + k]);
     const int row0 = blockIdx.x * 32 + threadIdx.x * 16;
-    ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = mn;
-    ccol[(row0 >> 8) * kTileC + kTileDb + kTileDb / kChunk + ((row0 & 255) >> 4)] = mx;
+    ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = m;
   }
 }
 
@@ -167,108 +151,60 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
   return Pair2{min(a.lo, b.lo), __vimin3_s32(max(a.lo, b.lo), a.hi, b.hi)};
 }
 
-// ---- epilogue, stage 1: the filter.  One step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot
-// products x = q.d.  With T a valid upper bound on this query's final 2nd-smallest t = ||d||^2 - 2 q.d (ties admitted):
-//   some row of the chunk can still enter the top-2   =>   min_norm(chunk) - 2*max(x) <= T.
-// 8 three-input max ops + 1 IMAD + 1 compare + 1 vote per 16 rows, no shared-memory traffic.  A lane that passes
-//   (a) pushes the chunk's 16 raw dot products onto its warp's candidate stack in shared memory -- the exact top-2 work
-//       is NOT done here, where 31 of 32 lanes would idle through it;
-//   (b) tightens T right away from an upper bound: the chunk's best row has t <= u = max_norm(chunk) - 2*max(x), and the
-//       2nd-smallest u over distinct chunks bounds the 2nd-smallest t.  So T never waits for the deferred stage.
-// Exactness: the test is necessary for membership in the final top-2, so every needed row is pushed.
-struct FilterState {
-  int b1, b2;   // two smallest upper bounds u seen by this thread in this item (distinct chunks = distinct rows)
-  int T;        // min(b2, exact 2nd best so far, what the other warps of these queries published)
-  int count;    // warp-uniform: entries on this warp's candidate stack
-};
-
-__device__ __forceinline__ bool filter_chunk16(const int32_t* __restrict__ x, const int cmin, const int cmax, const int two,
-                                               const int meta, const uint32_t queue_saddr, const uint32_t bound_saddr,
-                                               FilterState& f) {
+// One filter step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot products x = q.d:
+//   some row of the chunk can still enter the top-2  =>  min_norm(chunk) - 2*max(x) <= T   (T: best-known 2nd-smallest
+//   t = ||d||^2 - 2 q.d of this query, ties admitted).  10 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
+//   shared-memory traffic.  Only when some lane of the warp passes is the chunk examined in groups of 4, and only for the
+//   groups that pass are exact packed keys ((||d||^2 - 2x) << 8 | col, one IMAD each) formed and merged (top-2 of 4 by
+//   a small sorting network) into the tile's running top-2.
+// Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
+// by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
+__device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
+                                            const int g1t, const uint32_t bound_saddr, const int two, int& l1, int& l2,
+                                            int& T) {
 #if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
-  f.b1 = min(f.b1, x[0]);
-  return false;
+  l1 = min(l1, x[0]);
+  return;
 #endif
-  const int a0 = __vimax3_s32(x[0], x[1], x[2]);
-  const int a1 = __vimax3_s32(x[3], x[4], x[5]);
-  const int a2 = __vimax3_s32(x[6], x[7], x[8]);
-  const int a3 = __vimax3_s32(x[9], x[10], x[11]);
-  const int a4 = __vimax3_s32(x[12], x[13], x[14]);
-  const int m = max(__vimax3_s32(a0, a1, a2), __vimax3_s32(a3, a4, x[15]));
+  int g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
+  const int m = max(__vimax3_s32(g[0], g[1], g[2]), g[3]);
 #if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
-  f.b1 = min(f.b1, m + f.T + cmin + cmax);
-  return false;
+  l1 = min(l1, m + T + cmin);
+  return;
 #endif
-  const bool hit = two * m + f.T >= cmin;
-  const unsigned mask = __ballot_sync(0xffffffffu, hit);
   DBG_ADD(0, 1);
-  if (mask == 0) return false;
-  DBG_ADD(1, 1);
-  DBG_ADD(3, __popc(mask));
-  if (hit) {
-    const unsigned lane_lt = (1u << (threadIdx.x & 31)) - 1u;
-    const uint32_t e = queue_saddr + (f.count + __popc(mask & lane_lt)) * (kEntryInts * 4);
-    ptx::sts128(e, make_int4(x[0], x[1], x[2], x[3]));
-    ptx::sts128(e + 16, make_int4(x[4], x[5], x[6], x[7]));
-    ptx::sts128(e + 32, make_int4(x[8], x[9], x[10], x[11]));
-    ptx::sts128(e + 48, make_int4(x[12], x[13], x[14], x[15]));
-    ptx::sts32(e + 64, meta);
-    const int u = cmax - two * m;
-    f.b2 = min(f.b2, max(f.b1, u));
-    f.b1 = min(f.b1, u);
-    if (f.b2 < f.T) {
-      f.T = f.b2;
-      ptx::red_min_shared(bound_saddr, f.T);  // the warps scanning the other columns of these queries see it now
+#if MVGCUDA_EXPERIMENT == 3
+  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, two * m + T >= cmin));  // all lanes vote, lane 0 records
+  DBG_ADD(3, dbg_lane_hits);
+#endif
+  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
+    DBG_ADD(1, 1);
+    // which groups of 4 rows can still matter (all four votes issued back to back)
+    const bool h0 = __any_sync(0xffffffffu, two * g[0] + T >= cmin);
+    const bool h1 = __any_sync(0xffffffffu, two * g[1] + T >= cmin);
+    const bool h2 = __any_sync(0xffffffffu, two * g[2] + T >= cmin);
+    const bool h3 = __any_sync(0xffffffffu, two * g[3] + T >= cmin);
+    const bool h[4] = {h0, h1, h2, h3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (h[k]) {
+        DBG_ADD(2, 1);
+        const int4 cc = ptx::lds128(cs_saddr + 16 * k);  // warp-uniform address: smem broadcast
+        const int p0 = static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(x[4 * k + 0]));
+        const int p1 = static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(x[4 * k + 1]));
+        const int p2 = static_cast<int>(static_cast<uint32_t>(cc.z) - 512u * static_cast<uint32_t>(x[4 * k + 2]));
+        const int p3 = static_cast<int>(static_cast<uint32_t>(cc.w) - 512u * static_cast<uint32_t>(x[4 * k + 3]));
+        const Pair2 c = merge2(sort2(p0, p1), sort2(p2, p3));
+        const int nl2 = __vimin3_s32(max(l1, c.lo), l2, c.hi);
+        l1 = min(l1, c.lo);
+        l2 = nl2;
+      }
     }
-  }
-  f.count += __popc(mask);
-  return f.count >= kFlushAt;
-}
-
-// ---- epilogue, stage 2: dense exact evaluation.  Each lane takes ONE stack entry (of any query of this warp), forms the 16
-// exact packed keys ((||d||^2 - 2x) << 8 | col; the per-row constants come from global memory / L2, the tile's copy in
-// shared memory may be gone by now), finds their top-2 with a sorting-network merge tree and folds it into the query's
-// running exact top-2 in shared memory with 64-bit atomic mins -- no ordering between lanes, warps or batches needed.
-__device__ __forceinline__ unsigned long long cand_key(int t, int row) {
-  return (static_cast<unsigned long long>(static_cast<uint32_t>(t) ^ 0x80000000u) << 32) | static_cast<uint32_t>(row);
-}
-__device__ __forceinline__ int cand_key_t(unsigned long long k) { return static_cast<int>(static_cast<uint32_t>(k >> 32) ^ 0x80000000u); }
-__device__ __forceinline__ int cand_key_row(unsigned long long k) { return static_cast<int>(static_cast<uint32_t>(k)); }
-
-__device__ __forceinline__ void process_batch(const uint32_t queue_saddr, const uint32_t best_saddr, const uint32_t second_saddr,
-                                              const int* __restrict__ ccol_item, const uint32_t bound_saddr, FilterState& f) {
-  const int lane = threadIdx.x & 31;
-  const int n = min(f.count, 32);
-  const int first = f.count - n;       // the top n entries of the stack
-  if (lane < n) {
-    const uint32_t e = queue_saddr + (first + lane) * (kEntryInts * 4);
-    const int meta = ptx::lds32(e + 64);  // tile << 9 | chunk-in-tile << 5 | owner lane
-    const int tile = meta >> 9;
-    const int4* cc = reinterpret_cast<const int4*>(ccol_item + (size_t)tile * kTileC + ((meta >> 5) & 15) * kChunk);
-    const int4 c0 = __ldg(cc), c1 = __ldg(cc + 1), c2 = __ldg(cc + 2), c3 = __ldg(cc + 3);
-    const int4 x0 = ptx::lds128(e), x1 = ptx::lds128(e + 16), x2 = ptx::lds128(e + 32), x3 = ptx::lds128(e + 48);
-#define MVG_KEY(c, x) static_cast<int>(static_cast<uint32_t>(c) - 512u * static_cast<uint32_t>(x))
-    const Pair2 m0 = merge2(sort2(MVG_KEY(c0.x, x0.x), MVG_KEY(c0.y, x0.y)), sort2(MVG_KEY(c0.z, x0.z), MVG_KEY(c0.w, x0.w)));
-    const Pair2 m1 = merge2(sort2(MVG_KEY(c1.x, x1.x), MVG_KEY(c1.y, x1.y)), sort2(MVG_KEY(c1.z, x1.z), MVG_KEY(c1.w, x1.w)));
-    const Pair2 m2 = merge2(sort2(MVG_KEY(c2.x, x2.x), MVG_KEY(c2.y, x2.y)), sort2(MVG_KEY(c2.z, x2.z), MVG_KEY(c2.w, x2.w)));
-    const Pair2 m3 = merge2(sort2(MVG_KEY(c3.x, x3.x), MVG_KEY(c3.y, x3.y)), sort2(MVG_KEY(c3.z, x3.z), MVG_KEY(c3.w, x3.w)));
-#undef MVG_KEY
-    const Pair2 c = merge2(merge2(m0, m1), merge2(m2, m3));
-    const int base = tile * kTileDb;
-    const unsigned long long k1 = cand_key(c.lo >> 8, base + (c.lo & 255));
-    const unsigned long long k2 = cand_key(c.hi >> 8, base + (c.hi & 255));
-    const uint32_t o = 8u * static_cast<uint32_t>(meta & 31);
-    const unsigned long long old = ptx::atom_min_u64_shared(best_saddr + o, k1);
-    ptx::red_min_u64_shared(second_saddr + o, old > k1 ? old : k1);  // whichever of (old best, this) is not the best
-    ptx::red_min_u64_shared(second_saddr + o, k2);
-  }
-  f.count = first;
-  __syncwarp();
-  // the exact running 2nd best is a valid bound too
-  const int t2 = cand_key_t(ptx::lds64_volatile(second_saddr + 8u * lane));
-  if (t2 < f.T) {
-    f.T = t2;
-    ptx::red_min_shared(bound_saddr, f.T);
+    // 2nd smallest t over {running top-2 of earlier tiles} U {this tile's top-2}
+    T = __vimin3_s32(T, max(g1t, l1 >> 8), l2 >> 8);
+    ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
   }
 }
 
@@ -277,37 +213,35 @@ constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overf
 // (t, index) lexicographic order: smaller distance first, lower db row on ties
 __device__ __forceinline__ bool cand_less(int ta, int ia, int tb, int ib) { return ta < tb || (ta == tb && ia < ib); }
 
-static_assert(sizeof(KnnSmem) + 1024 <= 232448, "KnnSmem exceeds the 227 KB opt-in shared memory of sm_100");
-
-// All shared-memory traffic of the kernel uses 32-bit shared-window addresses: one base + compile-time offsets.
-#define MVG_SOFF(field) static_cast<uint32_t>(offsetof(KnnSmem, field))
-
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 B
             const __grid_constant__ CUtensorMap tmap_db,  // box 256 rows x 128 B
             const KnnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t sb = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // KnnSmem lives here (1024-B aligned for the swizzle)
+  KnnSmem& s = *reinterpret_cast<KnnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
 #if MVGCUDA_EXPERIMENT == 3
   if (threadIdx.x < 8) dbg_smem()[threadIdx.x] = 0;
 #endif
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_db);
-    for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(sb + MVG_SOFF(a_full) + 8 * i, 1); ptx::mbar_init(sb + MVG_SOFF(a_empty) + 8 * i, 1); }
-    for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(sb + MVG_SOFF(b_full) + 8 * i, 1); ptx::mbar_init(sb + MVG_SOFF(b_empty) + 8 * i, 1); }
-    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(sb + MVG_SOFF(c_full) + 8 * i, 1); ptx::mbar_init(sb + MVG_SOFF(c_empty) + 8 * i, kNumEpiWarps); }
-    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(sb + MVG_SOFF(acc_full) + 8 * i, 1); ptx::mbar_init(sb + MVG_SOFF(acc_empty) + 8 * i, kNumEpiWarps); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(&s.a_full[i], 1); ptx::mbar_init(&s.a_empty[i], 1); }
+    for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(&s.b_full[i], 1); ptx::mbar_init(&s.b_empty[i], 1); }
+    // a tile is consumed by the 8 epilogue warps of one tile-parity group
+    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kNumEpiWarps / 2); }
+    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&s.acc_full[i], 1); ptx::mbar_init(&s.acc_empty[i], kNumEpiWarps / 2); }
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc_saddr<512>(sb + MVG_SOFF(tmem_base));
+  if (warp == 0) ptx::tmem_alloc<512>(&s.tmem_base);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = static_cast<uint32_t>(ptx::lds32(sb + MVG_SOFF(tmem_base)));
+  const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -318,20 +252,19 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         locate_item(p, item, job, qb);
         const PairJob J = p.jobs[job];
         const uint32_t sa = a_it % kSlotsA;
-        ptx::mbar_wait(sb + MVG_SOFF(a_empty) + 8 * sa, ((a_it / kSlotsA) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(sb + MVG_SOFF(a_full) + 8 * sa, kBytesA);
-        ptx::tma_load_2d(sb + MVG_SOFF(a) + sa * kBytesA, &tmap_q, 0, J.q_row0 + qb * kBlockQ, sb + MVG_SOFF(a_full) + 8 * sa);
+        ptx::mbar_wait(&s.a_empty[sa], ((a_it / kSlotsA) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&s.a_full[sa], kBytesA);
+        ptx::tma_load_2d(s.a[sa], &tmap_q, 0, J.q_row0 + qb * kBlockQ, &s.a_full[sa]);
         const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
         for (int t = 0; t < ntiles; ++t, ++b_it, ++c_it) {
           const uint32_t sc = c_it % kSlotsC;
-          ptx::mbar_wait(sb + MVG_SOFF(c_empty) + 8 * sc, ((c_it / kSlotsC) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(sb + MVG_SOFF(c_full) + 8 * sc, kBytesC);
-          ptx::bulk_load_1d(sb + MVG_SOFF(c) + sc * kBytesC, p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, kBytesC,
-                            sb + MVG_SOFF(c_full) + 8 * sc);
-          const uint32_t sbs = b_it % kStagesB;
-          ptx::mbar_wait(sb + MVG_SOFF(b_empty) + 8 * sbs, ((b_it / kStagesB) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(sb + MVG_SOFF(b_full) + 8 * sbs, kBytesB);
-          ptx::tma_load_2d(sb + MVG_SOFF(b) + sbs * kBytesB, &tmap_db, 0, J.db_row0 + t * kTileDb, sb + MVG_SOFF(b_full) + 8 * sbs);
+          ptx::mbar_wait(&s.c_empty[sc], ((c_it / kSlotsC) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&s.c_full[sc], kBytesC);
+          ptx::bulk_load_1d(s.c[sc], p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, kBytesC, &s.c_full[sc]);
+          const uint32_t sb = b_it % kStagesB;
+          ptx::mbar_wait(&s.b_empty[sb], ((b_it / kStagesB) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&s.b_full[sb], kBytesB);
+          ptx::tma_load_2d(s.b[sb], &tmap_db, 0, J.db_row0 + t * kTileDb, &s.b_full[sb]);
         }
       }
     }
@@ -346,107 +279,133 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         locate_item(p, item, job, qb);
         const int db_rows = p.jobs[job].db_rows;
         const uint32_t sa = a_it % kSlotsA;
-        ptx::mbar_wait(sb + MVG_SOFF(a_full) + 8 * sa, (a_it / kSlotsA) & 1);
-        const uint64_t adesc = ptx::make_kmajor_sw128_desc(sb + MVG_SOFF(a) + sa * kBytesA);
+        ptx::mbar_wait(&s.a_full[sa], (a_it / kSlotsA) & 1);
+        const uint64_t adesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s.a[sa]));
         const int ntiles = (db_rows + kTileDb - 1) / kTileDb;
         for (int t = 0; t < ntiles; ++t, ++b_it, ++acc_it) {
-          const uint32_t sbs = b_it % kStagesB;
+          const uint32_t sb = b_it % kStagesB;
           const uint32_t buf = acc_it % kAccBufs;
-          ptx::mbar_wait(sb + MVG_SOFF(b_full) + 8 * sbs, (b_it / kStagesB) & 1);
-          ptx::mbar_wait(sb + MVG_SOFF(acc_empty) + 8 * buf, ((acc_it / kAccBufs) & 1) ^ 1);
+          ptx::mbar_wait(&s.b_full[sb], (b_it / kStagesB) & 1);
+          ptx::mbar_wait(&s.acc_empty[buf], ((acc_it / kAccBufs) & 1) ^ 1);
           ptx::tc_fence_after();
-          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + MVG_SOFF(b) + sbs * kBytesB);
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s.b[sb]));
           const uint32_t tmem_d = tmem_base + buf * kTileDb;
 #pragma unroll
           for (int k = 0; k < kDim / 32; ++k)  // K = 32 bytes per kind::i8 instruction
             ptx::mma_i8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          ptx::mma_commit(sb + MVG_SOFF(b_empty) + 8 * sbs);   // db stage reusable once these MMAs have read it
-          ptx::mma_commit(sb + MVG_SOFF(acc_full) + 8 * buf);  // accumulator ready for the epilogue
+          ptx::mma_commit(&s.b_empty[sb]);    // db stage reusable once these MMAs have read it
+          ptx::mma_commit(&s.acc_full[buf]);  // accumulator ready for the epilogue
         }
-        ptx::mma_commit(sb + MVG_SOFF(a_empty) + 8 * sa);  // query slot reusable
+        ptx::mma_commit(&s.a_empty[sa]);  // query slot reusable
       }
     }
     __syncwarp();
   } else {
     // ===================== epilogue: kEpiParts threads per query row =====================
-    // Warp (quad, part) owns TMEM lanes 32*quad.. and columns [64*part, 64*part+64) of every tile.
+    // Warp (quad, half, par) owns TMEM lanes 32*quad.., columns [128*half, 128*half+128) of the tiles whose running
+    // accumulator index has parity `par` (those tiles always land in TMEM buffer `par`).  Two parities x two halves:
+    // per-tile fixed costs are paid once per 128 columns, and the two parity groups drift independently.
     const int quad = warp & 3;            // a warp may only touch its own TMEM lane quadrant
     const int part = (warp - kFirstEpiWarp) >> 2;
+    const int half = part & 1;
+    const uint32_t par = static_cast<uint32_t>(part >> 1);
     const int row = quad * 32 + lane;     // query row within the block
     const int two = p.two;
-    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * kPartCols;
-    const uint32_t queue_saddr = sb + MVG_SOFF(queue) + (warp - kFirstEpiWarp) * (kQueueCap * kEntryInts * 4);
-    const uint32_t cm_off = MVG_SOFF(c) + (kTileDb + part * (kPartCols / kChunk)) * 4;  // this part's 4 chunk minima in a C slot
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + par * kTileDb + half * kPartCols;
     uint32_t acc_it = 0, c_it = 0, item_it = 0;
-    ptx::sts32(sb + MVG_SOFF(bound) + 4 * row, kTInit);
-    ptx::sts32(sb + MVG_SOFF(bound) + 4 * (kBlockQ + row), kTInit);
-    ptx::sts64(sb + MVG_SOFF(best) + 8 * row, ~0ull);
-    ptx::sts64(sb + MVG_SOFF(best) + 8 * (kBlockQ + row), ~0ull);
-    ptx::sts64(sb + MVG_SOFF(second) + 8 * row, ~0ull);
-    ptx::sts64(sb + MVG_SOFF(second) + 8 * (kBlockQ + row), ~0ull);
+    s.bound[0][row] = kTInit;
+    s.bound[1][row] = kTInit;
     asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_it) {
       int job, qb;
       locate_item(p, item, job, qb);
       const PairJob J = p.jobs[job];
+      const int q_local = qb * kBlockQ + row;
+      const bool q_ok = q_local < J.q_rows;
       const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
-      FilterState f = {kTInit, kTInit, kTInit, 0};
-      const uint32_t ip = item_it & 1;
-      const uint32_t bound_saddr = sb + MVG_SOFF(bound) + 4 * (ip * kBlockQ + row);
-      const uint32_t best_saddr = sb + MVG_SOFF(best) + 8 * (ip * kBlockQ + quad * 32);      // this warp's 32 queries
-      const uint32_t second_saddr = sb + MVG_SOFF(second) + 8 * (ip * kBlockQ + quad * 32);
-      const int* ccol_item = p.ccol + (size_t)(J.db_row0 >> 8) * kTileC;
-      // the other parity's slots are idle (every part left the previous item at the barrier below): reset them for the next item
-      ptx::sts32(sb + MVG_SOFF(bound) + 4 * ((ip ^ 1) * kBlockQ + row), kTInit);
-      ptx::sts64(sb + MVG_SOFF(best) + 8 * ((ip ^ 1) * kBlockQ + row), ~0ull);
-      ptx::sts64(sb + MVG_SOFF(second) + 8 * ((ip ^ 1) * kBlockQ + row), ~0ull);
+      // running best two of this thread's columns in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
+      int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;
+      const uint32_t bound_saddr = ptx::smem_u32(&s.bound[item_it & 1][row]);
+      // the other parity's slot is idle (every part left the previous item at the barrier below): reset it for the next item
+      s.bound[(item_it & 1) ^ 1][row] = kTInit;
       for (int t = 0; t < ntiles; ++t, ++acc_it, ++c_it) {
-        const uint32_t buf = acc_it & 1u;
+        if ((acc_it & 1u) != par) continue;  // the other group's tile
         const uint32_t sc = c_it % kSlotsC;
-        ptx::mbar_wait(sb + MVG_SOFF(c_full) + 8 * sc, (c_it / kSlotsC) & 1);
-        ptx::mbar_wait(sb + MVG_SOFF(acc_full) + 8 * buf, (acc_it >> 1) & 1);
+        ptx::mbar_wait(&s.c_full[sc], (c_it / kSlotsC) & 1);
+        ptx::mbar_wait(&s.acc_full[par], (acc_it >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = taddr0 + buf * kTileDb;
-        int32_t va[16], vb[16];
-        ptx::tmem_ld_32x32b_x16(taddr, va);
-        const int4 mn = ptx::lds128(sb + cm_off + sc * kBytesC), mx = ptx::lds128(sb + cm_off + sc * kBytesC + 64);
-        const int meta = (t << 9) | (part << 7) | lane;  // + chunk-in-part << 5
-        f.T = min(f.T, ptx::lds32_volatile(bound_saddr));
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 16, vb);
-        if (filter_chunk16(va, mn.x, mx.x, two, meta, queue_saddr, bound_saddr, f))
-          process_batch(queue_saddr, best_saddr, second_saddr, ccol_item, bound_saddr, f);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 32, va);
-        if (filter_chunk16(vb, mn.y, mx.y, two, meta | (1 << 5), queue_saddr, bound_saddr, f))
-          process_batch(queue_saddr, best_saddr, second_saddr, ccol_item, bound_saddr, f);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x16(taddr + 48, vb);
-        f.T = min(f.T, ptx::lds32_volatile(bound_saddr));
-        if (filter_chunk16(va, mn.z, mx.z, two, meta | (2 << 5), queue_saddr, bound_saddr, f))
-          process_batch(queue_saddr, best_saddr, second_saddr, ccol_item, bound_saddr, f);
-        ptx::tmem_ld_wait();
-        // every column of this warp is in registers: hand the accumulator back to the MMA warp
+        const uint32_t cs = ptx::smem_u32(s.c[sc] + half * kPartCols);
+        int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;
+        int T = min(min(g2t, kTInit), ptx::lds32_volatile(bound_saddr));  // admit t <= T
+        const uint32_t cm_saddr = ptx::smem_u32(s.c[sc] + kTileDb + half * (kPartCols / kChunk));
+        const int4 cm0 = ptx::lds128(cm_saddr);
+        const int4 cm1 = ptx::lds128(cm_saddr + 16);
+        int32_t v0[16], v1[16], v2[16], v3[16];
+        // first 64 columns
+        ptx::tmem_ld_32x32b_x16(taddr, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
+        ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_wait_for(v2);
+        ptx::tmem_ld_wait_for(v3);
+        epi_chunk16(v0, cs, cm0.x, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 64, cm0.y, g1t, bound_saddr, two, l1, l2, T);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v2, cs + 128, cm0.z, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 192, cm0.w, g1t, bound_saddr, two, l1, l2, T);
+        // second 64 columns; once they are in registers the accumulator goes back to the MMA warp
+        ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 96, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 112, v3);
+        ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_wait_for(v2);
+        ptx::tmem_ld_wait_for(v3);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(sb + MVG_SOFF(acc_empty) + 8 * buf);
-          ptx::mbar_arrive(sb + MVG_SOFF(c_empty) + 8 * sc);  // the chunk minima/maxima are in registers too
+        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v0, cs + 256, cm1.x, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 320, cm1.y, g1t, bound_saddr, two, l1, l2, T);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        epi_chunk16(v2, cs + 384, cm1.z, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 448, cm1.w, g1t, bound_saddr, two, l1, l2, T);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
+        // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index
+        if (l1 != 0x7FFFFFFF) {
+          const int base = t * kTileDb;
+          const int t1 = l1 >> 8, i1 = base + (l1 & 255);
+          const int t2 = l2 >> 8, i2 = base + (l2 & 255);
+          if (t1 < g1t) {
+            if (t2 < g1t) { g2t = t2; g2i = i2; } else { g2t = g1t; g2i = g1i; }
+            g1t = t1; g1i = i1;
+          } else if (t1 < g2t) {
+            g2t = t1; g2i = i1;
+          }
         }
-        if (filter_chunk16(vb, mn.w, mx.w, two, meta | (3 << 5), queue_saddr, bound_saddr, f))
-          process_batch(queue_saddr, best_saddr, second_saddr, ccol_item, bound_saddr, f);
       }
-      if (f.count > 0) process_batch(queue_saddr, best_saddr, second_saddr, ccol_item, bound_saddr, f);
-      // every part has folded all of its candidates into the shared exact state: part 0 writes the records
+      // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record
+      if (part > 0) s.xchg[item_it & 1][part - 1][row] = make_int4(g1t, g1i, g2t, g2i);
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");  // the warps sharing these 32 queries
-      const int q_local = qb * kBlockQ + row;
-      if (part == 0 && q_local < J.q_rows) {
-        const unsigned long long k1 = ptx::lds64_volatile(sb + MVG_SOFF(best) + 8 * (ip * kBlockQ + row));
-        const unsigned long long k2 = ptx::lds64_volatile(sb + MVG_SOFF(second) + 8 * (ip * kBlockQ + row));
+      if (part == 0 && q_ok) {
+        int b1t = g1t, b1i = g1i, b2t = g2t, b2i = g2i;
+#pragma unroll
+        for (int o_ = 0; o_ < kEpiParts - 1; ++o_) {
+          const int4 o = s.xchg[item_it & 1][o_][row];
+          if (cand_less(o.x, o.y, b1t, b1i)) {
+            if (cand_less(o.z, o.w, b1t, b1i)) { b2t = o.z; b2i = o.w; } else { b2t = b1t; b2i = b1i; }
+            b1t = o.x; b1i = o.y;
+          } else if (cand_less(o.x, o.y, b2t, b2i)) {
+            b2t = o.x; b2i = o.y;
+          }
+        }
         const int qn = p.ccol[ccol_index(J.q_row0 + q_local)] >> 8;
         KnnRecord r;
-        r.idx1 = cand_key_row(k1); r.idx2 = cand_key_row(k2);
-        r.d1 = qn + cand_key_t(k1); r.d2 = qn + cand_key_t(k2);
+        r.idx1 = b1i; r.idx2 = b2i; r.d1 = qn + b1t; r.d2 = qn + b2t;
         *reinterpret_cast<int4*>(&p.out[J.out_off + q_local]) = *reinterpret_cast<const int4*>(&r);
       }
     }

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+
 namespace mvgcuda {
 namespace ptx {
 
@@ -17,6 +19,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -25,6 +30,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -43,6 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -71,10 +96,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 63u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) {
+        printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // Explicit shared-space loads (a generic pointer into shared memory makes the compiler emit generic LD).
 __device__ __forceinline__ int4 lds128(uint32_t saddr) {
   int4 r;
-  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
   return r;
 }
 __device__ __forceinline__ int lds32(uint32_t saddr) {
@@ -86,6 +127,46 @@ __device__ __forceinline__ int lds32_volatile(uint32_t saddr) {
   int r;
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
   return r;
+}
+__device__ __forceinline__ unsigned long long atom_min_u64_shared(uint32_t saddr, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.shared.min.u64 %0, [%1], %2;" : "=l"(old) : "r"(saddr), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void red_min_u64_shared(uint32_t saddr, unsigned long long v) {
+  asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds64_volatile(uint32_t saddr) {
+  unsigned long long r;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(r) : "r"(saddr) : "memory");
+  return r;
+}
+// predicated forms: no branch at the C++ level, so the compiler keeps straight-line code around them
+__device__ __forceinline__ void sts128_if(bool pred, uint32_t saddr, const int4& v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.s32 [%0], {%1, %2, %3, %4};\n\t}"
+               ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(static_cast<int>(pred)) : "memory");
+}
+__device__ __forceinline__ void sts32_if(bool pred, uint32_t saddr, int v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.s32 [%0], %1;\n\t}"
+               ::"r"(saddr), "r"(v), "r"(static_cast<int>(pred)) : "memory");
+}
+__device__ __forceinline__ void red_min_shared_if(bool pred, uint32_t saddr, int v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.shared.min.s32 [%0], %1;\n\t}"
+               ::"r"(saddr), "r"(v), "r"(static_cast<int>(pred)) : "memory");
+}
+__device__ __forceinline__ void st_release_shared(uint32_t saddr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts64(uint32_t saddr, unsigned long long v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const int4& v) {
+  asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void red_min_shared(uint32_t saddr, int v) {
   asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -106,6 +187,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 // 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-B aligned).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                              uint64_t* bar) {
@@ -121,6 +214,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "n"(kCols)
                : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_saddr(uint32_t smem_result) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(kCols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 template <uint32_t kCols>
@@ -170,6 +268,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread i <-> lane i of
 // the warp's quadrant; v[j] <-> column j).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int32_t (&v)[32]) {
@@ -194,8 +296,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int32_t (&v)[
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Same, and makes the data dependency visible to the compiler: the registers of an earlier tcgen05.ld are only valid
-// after the wait, so they pass through it as in/out operands (nothing that reads them can be hoisted above it).
+// Same, and makes the data dependency visible to the compiler: the 16 registers of an earlier tcgen05.ld are only
+// valid after the wait, so they pass through it as in/out operands (nothing that reads them can be hoisted above it).
 __device__ __forceinline__ void tmem_ld_wait_for(int32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
