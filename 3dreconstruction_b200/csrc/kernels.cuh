@@ -375,17 +375,20 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         epi_chunk16(v3, cs + 448, cm1.w, g1t, bound_saddr, two, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
-        // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index
-        if (l1 != 0x7FFFFFFF) {
+        // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index.  Branch-free (selects):
+        // a lane-divergent branch here costs more than the dozen ALU ops.  An untouched l1/l2 (0x7FFFFFFF) decodes to
+        // t = 0x7FFFFF, larger than any real t, so it can only land in a slot that a real row later replaces.
+        {
           const int base = t * kTileDb;
           const int t1 = l1 >> 8, i1 = base + (l1 & 255);
           const int t2 = l2 >> 8, i2 = base + (l2 & 255);
-          if (t1 < g1t) {
-            if (t2 < g1t) { g2t = t2; g2i = i2; } else { g2t = g1t; g2i = g1i; }
-            g1t = t1; g1i = i1;
-          } else if (t1 < g2t) {
-            g2t = t1; g2i = i1;
-          }
+          const bool a = t1 < g1t, b = t2 < g1t, c = t1 < g2t;
+          const int n2t = a ? (b ? t2 : g1t) : (c ? t1 : g2t);
+          const int n2i = a ? (b ? i2 : g1i) : (c ? i1 : g2i);
+          g1t = a ? t1 : g1t;
+          g1i = a ? i1 : g1i;
+          g2t = n2t;
+          g2i = n2i;
         }
       }
       // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record

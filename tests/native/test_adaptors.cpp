@@ -4,6 +4,7 @@
 // binary travels to the GPU box.  Usage: test_adaptors <match_dir> <name1> <name2> ...   (names of images whose
 // .feat/.desc live in match_dir).  Exit code 0 and "ADAPTORS OK" on success.
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -20,6 +21,7 @@ using namespace mvg::utils;
 #include "mvg/feature/indexed_match_utils.h"
 #include "mvg/feature/matcher_all_in_memory.h"
 #include "mvg/feature/matcher_brute_force.h"
+#include "mvg/feature/two_view_matches.h"
 #include "mvgcuda/array_matcher_cuda.h"
 #include "mvgcuda/matcher_cuda_all_in_memory.h"
 
@@ -38,6 +40,23 @@ static std::vector<unsigned char> rnd(int rows, int alphabet, unsigned seed) {
   std::vector<unsigned char> v((size_t)rows * 128);
   for (auto& b : v) b = (unsigned char)(g() % alphabet);
   return v;
+}
+
+// the two-view entry GetPutativesMatches<DescriptorT, MatcherT> (two_view_matches.h:9-47, used by
+// apps/sift_match/sift_match.cpp:89-99) with the CUDA matcher as MatcherT, against the brute-force matcher.
+static void two_view(int nL, int nR, int alphabet, unsigned seed, float ratio) {
+  std::vector<unsigned char> l = rnd(nL, alphabet, seed), r = rnd(nR, alphabet, seed + 1);
+  std::vector<DescriptorT> L(nL), R(nR);
+  for (int i = 0; i < nL; ++i) memcpy(L[i].getData(), l.data() + (size_t)i * 128, 128);
+  for (int i = 0; i < nR; ++i) memcpy(R[i].getData(), r.data() + (size_t)i * 128, 128);
+  std::vector<IndexedMatch> m0, m1;
+  GetPutativesMatches<DescriptorT, MatcherBF>(L, R, mvg::math::Square(ratio), m0);
+  GetPutativesMatches<DescriptorT, ArrayMatcherCuda<unsigned char, MetricT> >(L, R, mvg::math::Square(ratio), m1);
+  CHECK(m0.size() == m1.size());
+  bool same = m0.size() == m1.size();
+  for (size_t k = 0; same && k < m0.size(); ++k) same = (m0[k] == m1[k]);
+  CHECK(same);
+  std::cout << "two-view " << nL << "x" << nR << " ratio " << ratio << ": " << m0.size() << " matches, identical=" << same << std::endl;
 }
 
 static void array_level(int db_rows, int nq, int alphabet, unsigned seed) {
@@ -62,6 +81,8 @@ int main(int argc, char** argv) {
   array_level(1000, 513, 3, 2);
   array_level(2, 5, 2, 3);
   array_level(1, 4, 256, 4);   // k=2 > rows: both return false, outputs untouched
+  two_view(700, 650, 4, 21, 0.8f);
+  two_view(1500, 1200, 256, 22, 0.95f);
   {
     ArrayMatcherCuda<unsigned char, MetricT> gpu;
     CHECK(!gpu.Build(NULL, 0, 128));
