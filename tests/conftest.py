@@ -18,7 +18,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def pkg():
-    return importlib.import_module("3dreconstruction_b200")
+    mod = importlib.import_module("3dreconstruction_b200")
+    if not os.path.exists(mod.mvgcuda.LIB_PATH):  # fresh checkout: compile libmvgcuda.so (nvcc cross-compiles without a GPU)
+        import __graft_entry__ as g
+        g.build()
+    return mod
 
 
 @pytest.fixture(scope="session")
