@@ -344,6 +344,17 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     rc = launch_knn(ctx, A, bp);
     if (rc) return rc;
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (ratio_sq > 1.0f) {
+      // For ratio > 1 a tie d1 == d2 passes the test, so WHICH of the tied rows is reported matters: reproduce the
+      // reference's std::partial_sort choice exactly (one extra CUDA-core pass per pair; the usual ratios <= 1 skip it).
+      for (int k = 0; k < nb; ++k) {
+        const PairJob& J = ctx->h_jobs.p[k];
+        if (!J.valid) continue;
+        tie_fixup_kernel<<<(J.q_rows + 7) / 8, 256, 0, st>>>(A.desc.p, J, ctx->d_knn.p);
+        ++launches;
+      }
+      CU_CHECK(ctx, cudaGetLastError());
+    }
     ratio_filter_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_jobs.p, ctx->d_knn.p, ratio_sq, ctx->d_tmp.p,
                                                         ctx->d_npass.p, ctx->d_counts.p);
     CU_CHECK(ctx, cudaGetLastError());

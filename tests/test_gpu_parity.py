@@ -307,3 +307,18 @@ def test_ragged_collection_many_sizes(ctx, pkg, l1):
     res = ctx.match_pairs(pairs, rs)
     for p, (i, j) in enumerate(pairs):
         assert np.array_equal(res.pair(p), l1.pair_matches(descs[i], descs[j], rs)), (sizes[i], sizes[j])
+
+
+def test_ratio_above_one_uses_reference_tie_rule(ctx, pkg, l1):
+    """With ratio > 1 a tie d1 == d2 passes the ratio test, so the reported _i depends on the tie rule: the pair path
+    must then reproduce the reference's std::partial_sort choice (SURVEY.md 8(a) rows 9-10)."""
+    descs = [synth.tie_set(301, 900, 2), synth.tie_set(302, 700, 2), synth.tie_set(303, 257, 3)]
+    ctx.upload_images(descs)
+    pairs = pkg.pairs_exhaustive(3)
+    for r in (1.0, 1.2):
+        rs = float(pkg.square_f32(r))
+        res = ctx.match_pairs(pairs, rs)
+        for p, (i, j) in enumerate(pairs):
+            assert np.array_equal(res.pair(p), l1.pair_matches(descs[i], descs[j], rs)), (i, j, r)
+        if r > 1:
+            assert res.counts.sum() > 100
