@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <shared_mutex>
 #include <cstdarg>
 #include <cstdio>
@@ -205,8 +206,10 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   CU_CHECK(ctx, cudaMemsetAsync(A.desc.p, 0, (size_t)A.arena_rows * kDim, st));
   for (int i = 0; i < n_images; ++i) {
     if (rows[i] == 0) continue;
+    // cudaMemcpyDefault: desc[i] may be host memory (pageable or pinned) or device memory (e.g. a replica that
+    // arrived over NVLink) -- unified addressing sorts it out
     CU_CHECK(ctx, cudaMemcpyAsync(A.desc.p + (size_t)A.row0[i] * kDim, desc[i], (size_t)rows[i] * kDim,
-                                  cudaMemcpyHostToDevice, st));
+                                  cudaMemcpyDefault, st));
   }
   (void)pinned;
   CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -474,16 +477,52 @@ struct DecoratedLess {
   }
 };
 
-static void dedup_xy(const float* fI, const float* fJ, const int* m, int n, std::vector<int>& out) {
-  std::vector<DecoratedMatch> v(n);
+// Bump allocator for the set's nodes: the container, its comparator and its insertion sequence are exactly the
+// reference's (so is the resulting tree); only where the nodes live changes -- one malloc per pair instead of one per
+// match.  deallocate() is a no-op, the arena is rewound by the owner after the set is gone.
+struct NodeArena {
+  std::vector<char> buf;
+  size_t used = 0;
+  void* take(size_t bytes, size_t align) {
+    size_t p = (used + align - 1) / align * align;
+    if (p + bytes > buf.size()) return nullptr;
+    used = p + bytes;
+    return buf.data() + p;
+  }
+};
+template <typename T>
+struct ArenaAlloc {
+  typedef T value_type;
+  NodeArena* arena;
+  explicit ArenaAlloc(NodeArena* a) : arena(a) {}
+  template <typename U>
+  ArenaAlloc(const ArenaAlloc<U>& o) : arena(o.arena) {}
+  T* allocate(size_t n) {
+    void* p = arena->take(n * sizeof(T), alignof(T));
+    if (!p) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T*, size_t) {}
+  template <typename U> bool operator==(const ArenaAlloc<U>& o) const { return arena == o.arena; }
+  template <typename U> bool operator!=(const ArenaAlloc<U>& o) const { return arena != o.arena; }
+};
+
+static void dedup_xy(const float* fI, const float* fJ, const int* m, int n, std::vector<int>& out, NodeArena& arena,
+                     std::vector<DecoratedMatch>& v) {
+  v.resize(n);
   for (int k = 0; k < n; ++k) {
     const int I = m[2 * k], J = m[2 * k + 1];
     v[k] = DecoratedMatch{fI[2 * I], fI[2 * I + 1], fJ[2 * J], fJ[2 * J + 1], I, J};
   }
-  std::set<DecoratedMatch, DecoratedLess> s(v.begin(), v.end());
+  if (arena.buf.size() < (size_t)n * 96 + 256) arena.buf.resize((size_t)n * 96 + 256);  // rb-tree node = 32 B header + 24 B payload
+  arena.used = 0;
   out.clear();
-  out.reserve(2 * s.size());
-  for (const DecoratedMatch& d : s) { out.push_back(d.i); out.push_back(d.j); }
+  {
+    typedef std::set<DecoratedMatch, DecoratedLess, ArenaAlloc<DecoratedMatch> > Set;
+    Set s(v.begin(), v.end(), DecoratedLess(), ArenaAlloc<DecoratedMatch>(&arena));  // same range construction as the reference (:93-95)
+    out.reserve(2 * s.size());
+    for (const DecoratedMatch& d : s) { out.push_back(d.i); out.push_back(d.j); }
+  }
 }
 
 }  // namespace mvgcuda
@@ -634,6 +673,8 @@ int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* p
   std::shared_mutex results_mtx;
   auto work = [&]() {
     std::vector<int> tmp;
+    NodeArena arena;
+    std::vector<DecoratedMatch> deco;
     for (;;) {
       const int64_t p = cursor.fetch_add(1);
       if (p >= n_pairs) break;
@@ -645,7 +686,8 @@ int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* p
       const int I = pairs[2 * p], J = pairs[2 * p + 1];
       {
         std::shared_lock<std::shared_mutex> lk(results_mtx);
-        dedup_xy(ctx->feats[I].data(), ctx->feats[J].data(), ctx->r_matches.p + 2 * ctx->r_offsets.p[p], ctx->r_counts.p[p], tmp);
+        dedup_xy(ctx->feats[I].data(), ctx->feats[J].data(), ctx->r_matches.p + 2 * ctx->r_offsets.p[p], ctx->r_counts.p[p], tmp,
+                 arena, deco);
       }
       per_pair[p] = tmp;
     }

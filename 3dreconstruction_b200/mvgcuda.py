@@ -207,6 +207,18 @@ class Context:
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rows, int(pinned)), "mvgcuda_upload_images")
         self._rows = [m.shape[0] for m in mats]
 
+    def upload_images_device(self, device_ptrs: Sequence[int], rows: Sequence[int]) -> None:
+        """Same as upload_images, from descriptor arrays that already live in device memory (raw CUDA pointers, e.g.
+        ``tensor.data_ptr()`` of a [rows][128] uint8 tensor on any GPU of the box)."""
+        n = len(rows)
+        ptrs = (C.POINTER(C.c_uint8) * max(n, 1))()
+        rws = (C.c_int32 * max(n, 1))()
+        for k in range(n):
+            ptrs[k] = C.cast(C.c_void_p(int(device_ptrs[k])), C.POINTER(C.c_uint8)) if rows[k] else None
+            rws[k] = int(rows[k])
+        self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rws, 0), "mvgcuda_upload_images")
+        self._rows = [int(r) for r in rows]
+
     def set_features(self, feats_xy: Sequence[np.ndarray]) -> None:
         mats = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy]
         n = len(mats)

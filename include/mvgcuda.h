@@ -79,7 +79,9 @@ int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
  * and ArrayMatcherBruteForce::Build, matcher_brute_force.h:42-50 -- but COPIES, so the caller
  * may free its buffers).  Replaces any previously uploaded set.  rows[i] >= 0; desc[i] may be
  * NULL when rows[i] == 0.  Also runs the per-row squared-norm kernel.
- * `pinned` != 0 promises that the desc buffers are page-locked (async H2D). */
+ * desc[i] may point to host memory (pageable or page-locked) or to DEVICE memory of any GPU of the box (unified
+ * addressing; used to fan a replica out over NVLink instead of re-reading it over PCIe on every GPU).
+ * `pinned` != 0 promises that host buffers are page-locked (async H2D). */
 int mvgcuda_upload_images(mvgcuda_ctx* ctx, int n_images, const uint8_t* const* desc,
                           const int32_t* rows, int pinned);
 int mvgcuda_num_images(const mvgcuda_ctx* ctx);
