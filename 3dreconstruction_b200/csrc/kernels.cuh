@@ -82,6 +82,9 @@ struct KnnParams {
   int n_items;
   KnnRecord* __restrict__ out;
   int two;  // always 2; a run-time value so that 2*x+T stays an IMAD (idle FMA pipe) instead of an IADD3 (ALU pipe, the bottleneck)
+  // Ratio-aware pruning (see epi_chunk16): the fp32 squared ratio of the Lowe test the records feed, or FLT_MAX when the
+  // caller needs the exact 2nd neighbour of EVERY query (array-level API, ratio > 1 with the tie fix-up).
+  float prune_ratio;
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -160,8 +163,8 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
 // Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
 // by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
 __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
-                                            const int g1t, const uint32_t bound_saddr, const int two, int& l1, int& l2,
-                                            int& T) {
+                                            const int g1t, const int g2t, const int qn, const float prune_ratio,
+                                            const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
 #if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
   l1 = min(l1, x[0]);
   return;
@@ -202,70 +205,20 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
         l2 = nl2;
       }
     }
-    // 2nd smallest t over {running top-2 of earlier tiles} U {this tile's top-2}
-    T = __vimin3_s32(T, max(g1t, l1 >> 8), l2 >> 8);
+    // Smallest (c1) and 2nd smallest (c2) t over {running top-2 of earlier tiles} U {this tile's top-2}: two rows this
+    // warp has really seen.  Rows with t > c2 can never enter the top-2.  Ratio-aware pruning goes further: when c1
+    // already fails the Lowe test against c2 (d1 >= ratio * d2, the reference's fp32 expression), rows with c1 < t <= c2
+    // cannot matter either -- such a row could only become the FINAL 2nd neighbour, and then d2 <= c2 makes the query fail
+    // the test whether it is recorded or not; and if a better 1st neighbour turns up later, the 2nd neighbour is at most
+    // c1.  So the bound drops to c1: the record's idx1/d1 stay exact for every query, d2/idx2 stay exact for every query
+    // that passes, and a failing query keeps a d2 that still fails (DESIGN.md "ratio-aware pruning" has the proof).
+    const int l1t = l1 >> 8;
+    const int c1 = min(g1t, l1t);
+    const int c2 = __vimin3_s32(max(g1t, l1t), l2 >> 8, g2t);
+    const bool passes = __int2float_rn(qn + c1) < __fmul_rn(prune_ratio, __int2float_rn(qn + c2));
+    T = min(T, passes ? c2 : c1);
     ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
   }
-}
-
-#ifndef MVGCUDA_BATCH_FILTER
-#define MVGCUDA_BATCH_FILTER 0
-#endif
-// Exact part of the chunk step (see epi_chunk16), with the per-group maxima already formed.
-__device__ __forceinline__ void epi_chunk16_exact(const int32_t* __restrict__ x, const int* __restrict__ g,
-                                                  const uint32_t cs_saddr, const int cmin, const int g1t,
-                                                  const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
-  const bool h0 = __any_sync(0xffffffffu, two * g[0] + T >= cmin);
-  const bool h1 = __any_sync(0xffffffffu, two * g[1] + T >= cmin);
-  const bool h2 = __any_sync(0xffffffffu, two * g[2] + T >= cmin);
-  const bool h3 = __any_sync(0xffffffffu, two * g[3] + T >= cmin);
-  const bool h[4] = {h0, h1, h2, h3};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (h[k]) {
-      const int4 cc = ptx::lds128(cs_saddr + 16 * k);
-      const int p0 = static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(x[4 * k + 0]));
-      const int p1 = static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(x[4 * k + 1]));
-      const int p2 = static_cast<int>(static_cast<uint32_t>(cc.z) - 512u * static_cast<uint32_t>(x[4 * k + 2]));
-      const int p3 = static_cast<int>(static_cast<uint32_t>(cc.w) - 512u * static_cast<uint32_t>(x[4 * k + 3]));
-      const Pair2 c = merge2(sort2(p0, p1), sort2(p2, p3));
-      const int nl2 = __vimin3_s32(max(l1, c.lo), l2, c.hi);
-      l1 = min(l1, c.lo);
-      l2 = nl2;
-    }
-  }
-  T = __vimin3_s32(T, max(g1t, l1 >> 8), l2 >> 8);
-  ptx::red_min_shared(bound_saddr, T);
-}
-
-// Four chunks at once: every chunk's filter and vote is issued before the first branch, so a branch never waits on
-// the max-tree / vote latency of its own chunk.  The votes use the bound as of the batch start (conservative: the
-// bound only shrinks); the exact step re-tests its groups against the current one.
-__device__ __forceinline__ void epi_batch64(const int32_t* __restrict__ x0, const int32_t* __restrict__ x1,
-                                            const int32_t* __restrict__ x2, const int32_t* __restrict__ x3,
-                                            const uint32_t cs_saddr, const int cm0, const int cm1, const int cm2,
-                                            const int cm3, const int g1t, const uint32_t bound_saddr, const int two,
-                                            int& l1, int& l2, int& T) {
-  int ga[4], gb[4], gc[4], gd[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    ga[k] = max(__vimax3_s32(x0[4 * k], x0[4 * k + 1], x0[4 * k + 2]), x0[4 * k + 3]);
-    gb[k] = max(__vimax3_s32(x1[4 * k], x1[4 * k + 1], x1[4 * k + 2]), x1[4 * k + 3]);
-    gc[k] = max(__vimax3_s32(x2[4 * k], x2[4 * k + 1], x2[4 * k + 2]), x2[4 * k + 3]);
-    gd[k] = max(__vimax3_s32(x3[4 * k], x3[4 * k + 1], x3[4 * k + 2]), x3[4 * k + 3]);
-  }
-  const int ma = max(__vimax3_s32(ga[0], ga[1], ga[2]), ga[3]);
-  const int mb = max(__vimax3_s32(gb[0], gb[1], gb[2]), gb[3]);
-  const int mc = max(__vimax3_s32(gc[0], gc[1], gc[2]), gc[3]);
-  const int md = max(__vimax3_s32(gd[0], gd[1], gd[2]), gd[3]);
-  const bool a0 = __any_sync(0xffffffffu, two * ma + T >= cm0);
-  const bool a1 = __any_sync(0xffffffffu, two * mb + T >= cm1);
-  const bool a2 = __any_sync(0xffffffffu, two * mc + T >= cm2);
-  const bool a3 = __any_sync(0xffffffffu, two * md + T >= cm3);
-  if (a0) epi_chunk16_exact(x0, ga, cs_saddr, cm0, g1t, bound_saddr, two, l1, l2, T);
-  if (a1) epi_chunk16_exact(x1, gb, cs_saddr + 64, cm1, g1t, bound_saddr, two, l1, l2, T);
-  if (a2) epi_chunk16_exact(x2, gc, cs_saddr + 128, cm2, g1t, bound_saddr, two, l1, l2, T);
-  if (a3) epi_chunk16_exact(x3, gd, cs_saddr + 192, cm3, g1t, bound_saddr, two, l1, l2, T);
 }
 
 constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overflow and passes every chunk
@@ -383,6 +336,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       const int q_local = qb * kBlockQ + row;
       const bool q_ok = q_local < J.q_rows;
       const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
+      const int qn = p.ccol[ccol_index(J.q_row0 + min(q_local, J.q_rows - 1))] >> 8;  // ||q||^2 (dist = qn + t)
       // running best two of this thread's columns in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
       int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;
       const uint32_t bound_saddr = ptx::smem_u32(&s.bound[item_it & 1][row]);
@@ -410,15 +364,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::tmem_ld_wait_for(v1);
         ptx::tmem_ld_wait_for(v2);
         ptx::tmem_ld_wait_for(v3);
-#if MVGCUDA_BATCH_FILTER
-        epi_batch64(v0, v1, v2, v3, cs, cm0.x, cm0.y, cm0.z, cm0.w, g1t, bound_saddr, two, l1, l2, T);
-#else
-        epi_chunk16(v0, cs, cm0.x, g1t, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 64, cm0.y, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v0, cs, cm0.x, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 64, cm0.y, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 128, cm0.z, g1t, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 192, cm0.w, g1t, bound_saddr, two, l1, l2, T);
-#endif
+        epi_chunk16(v2, cs + 128, cm0.z, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 192, cm0.w, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
         // second 64 columns; once they are in registers the accumulator goes back to the MMA warp
         ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
         ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
@@ -432,15 +382,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-#if MVGCUDA_BATCH_FILTER
-        epi_batch64(v0, v1, v2, v3, cs + 256, cm1.x, cm1.y, cm1.z, cm1.w, g1t, bound_saddr, two, l1, l2, T);
-#else
-        epi_chunk16(v0, cs + 256, cm1.x, g1t, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 320, cm1.y, g1t, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v0, cs + 256, cm1.x, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 320, cm1.y, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 384, cm1.z, g1t, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 448, cm1.w, g1t, bound_saddr, two, l1, l2, T);
-#endif
+        epi_chunk16(v2, cs + 384, cm1.z, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 448, cm1.w, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index.  Branch-free (selects):
@@ -474,7 +420,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
             b2t = o.x; b2i = o.y;
           }
         }
-        const int qn = p.ccol[ccol_index(J.q_row0 + q_local)] >> 8;
         KnnRecord r;
         r.idx1 = b1i; r.idx2 = b2i; r.d1 = qn + b1t; r.d2 = qn + b2t;
         *reinterpret_cast<int4*>(&p.out[J.out_off + q_local]) = *reinterpret_cast<const int4*>(&r);

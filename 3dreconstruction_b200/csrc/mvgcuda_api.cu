@@ -7,6 +7,7 @@
 // compacted matches travel back over PCIe.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cfloat>
 
 #include <algorithm>
 #include <atomic>
@@ -255,7 +256,7 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
   bp.n_records = rec;
 }
 
-static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp) {
+static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, float prune_ratio) {
   if (bp.n_items == 0) return MVGCUDA_OK;
   KnnParams kp;
   kp.ccol = A.ccol.p;
@@ -265,6 +266,7 @@ static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp) {
   kp.n_items = bp.n_items;
   kp.out = ctx->d_knn.p;
   kp.two = 2;
+  kp.prune_ratio = prune_ratio;
   const int grid = std::min(bp.n_items, ctx->prop.multiProcessorCount);
   knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(A.tmap_q, A.tmap_db, kp);
   CU_CHECK(ctx, cudaGetLastError());
@@ -344,7 +346,9 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_item_start.p, ctx->h_item_start.p, (nb + 1) * sizeof(int),
                                   cudaMemcpyHostToDevice, st));
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], st));
-    rc = launch_knn(ctx, A, bp);
+    // ratio <= 1: records only have to carry what the ratio test and the match list need (ratio-aware pruning);
+    // ratio > 1 keeps the exact 2nd neighbour of every query for the tie fix-up below
+    rc = launch_knn(ctx, A, bp, (ratio_sq <= 1.0f) ? ratio_sq : FLT_MAX);
     if (rc) return rc;
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));
     if (ratio_sq > 1.0f) {
@@ -436,7 +440,7 @@ static int knn2_impl(mvgcuda_ctx* ctx, const Arena& A, int db_img, int q_img, in
   cudaStream_t st = ctx->stream;
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jobs.p, ctx->h_jobs.p, sizeof(PairJob), cudaMemcpyHostToDevice, st));
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_item_start.p, ctx->h_item_start.p, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
-  rc = launch_knn(ctx, A, bp);
+  rc = launch_knn(ctx, A, bp, FLT_MAX);  // exact 2-NN of every query
   if (rc) return rc;
   if (tie_mode == MVGCUDA_TIE_REFERENCE) {
     const int warps_per_block = 8;

@@ -111,6 +111,9 @@ int mvgcuda_knn2_arrays(mvgcuda_ctx* ctx, const uint8_t* db, int db_rows, const 
  * the reference computes, Square(float distRatio) (numeric.h:108-111): pass r*r evaluated in
  * float, NOT float(double(r)*r).  Pairs whose images have < 2 db rows or < 1 query rows yield
  * zero matches (reference: SearchNeighbours returns false / empty, Appendix B of SURVEY.md).
+ * The surviving matches are bit-identical to the reference's for every ratio.  Internally, for ratio_sq <= 1 the kernel
+ * prunes rows that can change neither a ratio-test decision nor a reported index ("ratio-aware
+ * pruning"); the exact 2 nearest neighbours of EVERY query are what mvgcuda_knn2 / mvgcuda_knn2_arrays return.
  *
  * Result storage is owned by the context and valid until the next match_* / upload / destroy:
  *   counts[p]            matches of pair p

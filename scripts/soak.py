@@ -12,8 +12,10 @@ n_cases = int(os.environ.get("CASES", "150"))
 bad = 0
 t0 = time.time()
 for case in range(n_cases):
-    kind = rng.integers(0, 4)
+    kind = rng.integers(0, 5)
     n_db = int(rng.integers(2, 3000)); n_q = int(rng.integers(1, 2000))
+    if case % 25 == 24:
+        n_db = int(rng.integers(3000, 12000))   # many db tiles: long scans, all four column/tile parts busy
     if kind == 0:
         alpha = int(rng.choice([2, 3, 4, 8, 16]))
         db = rng.integers(0, alpha, (n_db, 128), dtype=np.uint8); q = rng.integers(0, alpha, (n_q, 128), dtype=np.uint8)
@@ -23,6 +25,14 @@ for case in range(n_cases):
         db = (rng.random((n_db, 128)) < 0.05).astype(np.uint8) * rng.integers(1, 256, (n_db, 128), dtype=np.uint8)
         q = (rng.random((n_q, 128)) < 0.05).astype(np.uint8) * rng.integers(1, 256, (n_q, 128), dtype=np.uint8)
         db[rng.integers(0, n_db, n_db // 4)] = db[rng.integers(0, n_db, n_db // 4)]
+    elif kind == 4:   # clusters: every query has several near copies in the db at different noise levels, scattered over
+        # the scan order, so d1/d2 sits on both sides of the ratio threshold (exercises the ratio-aware pruning rule)
+        base = pkg.synth.image(700 + case, 0, max(2, n_db // 4), np.zeros((0, 128), np.uint8), shared=0.0)
+        src = rng.integers(0, len(base), n_db)
+        amp = rng.integers(0, 40, (n_db, 1))
+        db = np.clip(base[src].astype(np.int16) + rng.integers(-1, 2, (n_db, 128)) * amp, 0, 255).astype(np.uint8)
+        qs = rng.integers(0, len(base), n_q)
+        q = np.clip(base[qs].astype(np.int16) + rng.integers(-1, 2, (n_q, 128)) * rng.integers(0, 12, (n_q, 1)), 0, 255).astype(np.uint8)
     else:             # SIFT-like with queries that are noisy copies of db rows
         db = pkg.synth.image(900 + case, 0, n_db, np.zeros((0, 128), np.uint8), shared=0.0)
         src = rng.integers(0, n_db, n_q)

@@ -143,6 +143,53 @@ def test_ratio_bit_pattern_matters(ctx, pkg, l1):
         assert np.array_equal(ctx.match_pairs(pairs, rs).pair(0), l1.pair_matches(descs[0], descs[1], rs))
 
 
+def _row_at_distance(qrow: np.ndarray, d: int, rng) -> np.ndarray:
+    """A u8 row at squared-L2 distance exactly d from qrow (qrow must leave +-11 of head-room in every bin)."""
+    delta = np.zeros(128, np.int16)
+    pos = rng.permutation(128)
+    k = 0
+    while d > 0:
+        v = min(11, int(np.sqrt(d)))
+        delta[pos[k]] = v if rng.random() < 0.5 else -v
+        d -= v * v
+        k += 1
+    return (qrow.astype(np.int16) + delta).astype(np.uint8)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ratio_aware_pruning_adversarial_orders(ctx, pkg, l1, seed):
+    """Scan orders built to break an unsound pruning rule: per query a handful of near rows
+    whose distances straddle the ratio threshold (e.g. 150, 200 early, then 130, then 90: the true pair (90, 130) fails
+    at 0.8^2 although (90, 150) would pass), scattered over tiles and column halves among far filler rows."""
+    rng = np.random.default_rng(4242 + seed)
+    n_q, n_db = 96, 2300
+    levels = rng.permutation(np.arange(20, 20 + 2 * n_q, 2))[:n_q]          # every query sits at its own grey level
+    q = np.repeat(levels[:, None], 128, axis=1).astype(np.uint8)
+    menu = [90, 100, 110, 128, 130, 140, 150, 160, 200, 250, 90, 141, 140, 157, 156]
+    dbs = []
+    for _ in range(6):
+        db = rng.integers(0, 256, (n_db, 128), dtype=np.uint8)                # fillers: distance ~ 1e6
+        slots = rng.permutation(n_db)
+        k = 0
+        for j in range(n_q):
+            for d in rng.choice(menu, int(rng.integers(2, 7)), replace=True):
+                db[slots[k]] = _row_at_distance(q[j], int(d), rng)
+                k += 1
+        dbs.append(db)
+    ctx.upload_images(dbs + [q])
+    pairs = np.array([[i, len(dbs)] for i in range(len(dbs))], np.int32)
+    for r in (0.8, 0.6, 0.95, 1.0):
+        rs = float(pkg.square_f32(r))
+        res = ctx.match_pairs(pairs, rs)
+        n_pass = 0
+        for p, (i, j) in enumerate(pairs):
+            want = l1.pair_matches(dbs[i], q, rs)
+            assert np.array_equal(res.pair(p), want), f"ratio {r} db {i}"
+            n_pass += len(want)
+        if r in (0.8, 0.95):
+            assert 0 < n_pass < len(pairs) * (n_q - 1)                        # both outcomes occur
+
+
 # ---------------------------------------------------------------- collection level + export (rows 7-14)
 
 @pytest.mark.parametrize("r", [0.6, 0.8])
