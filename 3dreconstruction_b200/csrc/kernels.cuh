@@ -75,7 +75,8 @@ struct KnnSmem {
 };
 
 struct KnnParams {
-  const int* __restrict__ ccol;        // K1 output, [arena_rows / 256][kTileC]
+  const int* __restrict__ ccol;        // K1 output, [arena_rows / 256][kTileC]: per-row constants of the db operand
+  const int* __restrict__ qcol;        // same layout for the rows the QUERY tensor map addresses (== ccol, except rescans)
   const PairJob* __restrict__ jobs;    // [n_jobs]
   const int* __restrict__ item_start;  // [n_jobs+1] prefix sum of query blocks per job
   int n_jobs;
@@ -85,6 +86,7 @@ struct KnnParams {
   // Ratio-aware pruning (see epi_chunk16): the fp32 squared ratio of the Lowe test the records feed, or FLT_MAX when the
   // caller needs the exact 2nd neighbour of EVERY query (array-level API, ratio > 1 with the tie fix-up).
   float prune_ratio;
+  float prune_rho;  // in (0, 1]: a failing query admits only rows with d <= rho * d(best); 1 = no rescans ever needed
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -163,7 +165,7 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
 // Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
 // by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
 __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
-                                            const int g1t, const int g2t, const int qn, const float prune_ratio,
+                                            const int g1t, const int g2t, const int qn, const float prune_ratio, const float prune_rho,
                                             const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
 #if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
   l1 = min(l1, x[0]);
@@ -216,7 +218,9 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
     const int c1 = min(g1t, l1t);
     const int c2 = __vimin3_s32(max(g1t, l1t), l2 >> 8, g2t);
     const bool passes = __int2float_rn(qn + c1) < __fmul_rn(prune_ratio, __int2float_rn(qn + c2));
-    T = min(T, passes ? c2 : c1);
+    // failing: admit d <= rho * d(c1), rounded up (rho = 1 gives exactly c1)
+    const int tf = __float2int_ru(__fmul_ru(prune_rho, __int2float_rn(qn + c1))) - qn;
+    T = min(T, passes ? c2 : tf);
     ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
   }
 }
@@ -336,7 +340,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       const int q_local = qb * kBlockQ + row;
       const bool q_ok = q_local < J.q_rows;
       const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
-      const int qn = p.ccol[ccol_index(J.q_row0 + min(q_local, J.q_rows - 1))] >> 8;  // ||q||^2 (dist = qn + t)
+      const int qn = p.qcol[ccol_index(J.q_row0 + min(q_local, J.q_rows - 1))] >> 8;  // ||q||^2 (dist = qn + t)
       // running best two of this thread's columns in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
       int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;
       const uint32_t bound_saddr = ptx::smem_u32(&s.bound[item_it & 1][row]);
@@ -364,11 +368,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::tmem_ld_wait_for(v1);
         ptx::tmem_ld_wait_for(v2);
         ptx::tmem_ld_wait_for(v3);
-        epi_chunk16(v0, cs, cm0.x, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 64, cm0.y, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v0, cs, cm0.x, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 64, cm0.y, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 128, cm0.z, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 192, cm0.w, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v2, cs + 128, cm0.z, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 192, cm0.w, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
         // second 64 columns; once they are in registers the accumulator goes back to the MMA warp
         ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
         ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
@@ -382,11 +386,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v0, cs + 256, cm1.x, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 320, cm1.y, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v0, cs + 256, cm1.x, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v1, cs + 320, cm1.y, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 384, cm1.z, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 448, cm1.w, g1t, g2t, qn, p.prune_ratio, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v2, cs + 384, cm1.z, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
+        epi_chunk16(v3, cs + 448, cm1.w, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index.  Branch-free (selects):
@@ -551,6 +555,75 @@ __device__ __forceinline__ int block_rank(bool flag, int* warp_tot /*[8] smem*/,
   return before + __popc(m & ((1u << lane) - 1u));
 }
 
+// ------------------------------------------------------------------------------------------ rescan of ambiguous queries
+// With prune_rho < 1 a failing query admits only rows with d <= rho * d(best).  Every row x skipped that way satisfies
+// d(x) > rho * d(B) (B = recorded 2nd neighbour), so a recorded pair (d1, d2) that passes the ratio
+// test is FINAL when it also passes against floor(rho * d2): no skipped row can bring d2 low enough to fail it.
+// Otherwise the query is ambiguous and is matched again, exactly, by a second knn2_kernel launch over the gathered rows.
+struct RescanSrc {
+  int src_out_off;  // first record / first entry of the flagged list of the original pair
+  int src_q_row0;   // arena row of query 0 of the original pair
+  int first;        // first entry of the flagged list this rescan job covers
+  int count;
+  int dst_row0;     // row in the rescan query buffer == record offset in the rescan record buffer
+};
+
+__device__ __forceinline__ bool ratio_pass(int d1, int d2, float ratio_sq) {
+  return __int2float_rn(d1) < __fmul_rn(ratio_sq, __int2float_rn(d2));  // DistanceRatioFilter, matching_filters.h:44
+}
+
+// One CTA per pair: ascending list of the ambiguous queries of the pair -> resc_idx[out_off + k], their number -> resc_cnt.
+__global__ void __launch_bounds__(kCompactThreads)
+flag_ambiguous_kernel(const PairJob* __restrict__ jobs, const KnnRecord* __restrict__ knn, float ratio_sq, float rho,
+                      int* __restrict__ resc_idx, int* __restrict__ resc_cnt) {
+  __shared__ int warp_tot[kCompactThreads / 32];
+  const PairJob J = jobs[blockIdx.x];
+  int base = 0;
+  if (J.valid) {
+    for (int q0 = 0; q0 < J.q_rows; q0 += kCompactThreads) {
+      const int q = q0 + threadIdx.x;
+      bool flag = false;
+      if (q < J.q_rows) {
+        const int4 r = *reinterpret_cast<const int4*>(&knn[J.out_off + q]);
+        if (ratio_pass(r.z, r.w, ratio_sq)) {
+          const int d_floor = __float2int_rd(__fmul_rd(rho, __int2float_rn(r.w)));
+          flag = !ratio_pass(r.z, d_floor, ratio_sq);
+        }
+      }
+      int tot;
+      const int rank = block_rank(flag, warp_tot, tot);
+      if (flag) resc_idx[J.out_off + base + rank] = q;
+      base += tot;
+    }
+  }
+  if (threadIdx.x == 0) resc_cnt[blockIdx.x] = base;
+}
+
+// One CTA per rescan job: copy the flagged queries (128 B each, 8 threads per row) and their norms into the rescan buffer.
+__global__ void __launch_bounds__(256)
+rescan_gather_kernel(const RescanSrc* __restrict__ src, const int* __restrict__ resc_idx, const uint8_t* __restrict__ arena,
+                     const int* __restrict__ ccol, uint8_t* __restrict__ dst, int* __restrict__ dst_ccol) {
+  const RescanSrc S = src[blockIdx.x];
+  const int part = threadIdx.x & 7;
+  for (int i = threadIdx.x >> 3; i < S.count; i += 32) {
+    const int row = S.src_q_row0 + resc_idx[S.src_out_off + S.first + i];
+    const uint4 v = *reinterpret_cast<const uint4*>(arena + (size_t)row * kDim + part * 16);
+    *reinterpret_cast<uint4*>(dst + (size_t)(S.dst_row0 + i) * kDim + part * 16) = v;
+    if (part == 0) dst_ccol[ccol_index(S.dst_row0 + i)] = ccol[ccol_index(row)];  // only the norm (bits 8..) is read
+  }
+}
+
+// One CTA per rescan job: exact records back to where the pruned ones were.
+__global__ void __launch_bounds__(256)
+rescan_scatter_kernel(const RescanSrc* __restrict__ src, const int* __restrict__ resc_idx,
+                      const KnnRecord* __restrict__ resc_knn, KnnRecord* __restrict__ knn) {
+  const RescanSrc S = src[blockIdx.x];
+  for (int i = threadIdx.x; i < S.count; i += 256) {
+    const int q = resc_idx[S.src_out_off + S.first + i];
+    *reinterpret_cast<int4*>(&knn[S.src_out_off + q]) = *reinterpret_cast<const int4*>(&resc_knn[S.dst_row0 + i]);
+  }
+}
+
 // K3a, one CTA per pair:
 //   (1) ratio test, fp32 exactly as DistanceRatioFilter: float(d1) < ratio_sq * float(d2)
 //   (2) ordered list of passing queries -> tmp[out_off + k] = (idx1, q)
@@ -569,7 +642,7 @@ ratio_filter_kernel(const PairJob* __restrict__ jobs, const KnnRecord* __restric
       if (q < J.q_rows) {
         const int4 r = *reinterpret_cast<const int4*>(&knn[J.out_off + q]);
         idx1 = r.x;
-        pass = __int2float_rn(r.z) < __fmul_rn(ratio_sq, __int2float_rn(r.w));
+        pass = ratio_pass(r.z, r.w, ratio_sq);
       }
       int tot;
       const int rank = block_rank(pass, warp_tot, tot);

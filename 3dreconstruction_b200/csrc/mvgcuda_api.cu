@@ -18,6 +18,7 @@
 #include <new>
 #include <shared_mutex>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <set>
@@ -85,6 +86,9 @@ struct PinnedBuf {
   }
 };
 
+constexpr float kDefaultPruneRho = 0.8f;
+constexpr int kDefaultRescanRows = 1 << 20;  // 128 MB of gathered queries per rescan round
+
 struct Arena {
   DevBuf<uint8_t> desc;   // [rows_padded][128]
   DevBuf<int> ccol;       // K1 output
@@ -121,6 +125,22 @@ struct mvgcuda_ctx {
   DevBuf<int2> d_matches;
   PinnedBuf<PairJob> h_jobs;
   PinnedBuf<int> h_item_start;
+
+  // ratio-aware pruning: admission factor for failing queries and the rescan of ambiguous ones
+  float prune_rho = kDefaultPruneRho;
+  int rescan_cap_rows = kDefaultRescanRows;
+  DevBuf<int> d_resc_idx, d_resc_cnt, d_resc_ccol, d_ritem_start;
+  DevBuf<uint8_t> d_resc_desc;
+  DevBuf<KnnRecord> d_resc_knn;
+  DevBuf<PairJob> d_rjobs;
+  DevBuf<RescanSrc> d_rsrc;
+  PinnedBuf<int> h_resc_cnt, h_ritem_start;
+  PinnedBuf<PairJob> h_rjobs;
+  PinnedBuf<RescanSrc> h_rsrc;
+  CUtensorMap tmap_resc;
+  const uint8_t* tmap_resc_base = nullptr;
+  int tmap_resc_rows = 0;
+  long long rescanned = 0;  // queries matched a second time by the last match call
   PinnedBuf<long long> h_total;
 
   // results of the last match call
@@ -256,10 +276,19 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
   bp.n_records = rec;
 }
 
-static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, float prune_ratio) {
-  if (bp.n_items == 0) return MVGCUDA_OK;
+static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp) {
+  if (kp.n_items == 0) return MVGCUDA_OK;
+  const int grid = std::min(kp.n_items, ctx->prop.multiProcessorCount);
+  knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
+  CU_CHECK(ctx, cudaGetLastError());
+  return MVGCUDA_OK;
+}
+
+// prune_ratio: the Lowe ratio the records will be tested against, or FLT_MAX for the exact 2-NN of every query.
+static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, float prune_ratio, float prune_rho) {
   KnnParams kp;
   kp.ccol = A.ccol.p;
+  kp.qcol = A.ccol.p;
   kp.jobs = ctx->d_jobs.p;
   kp.item_start = ctx->d_item_start.p;
   kp.n_jobs = bp.n_jobs;
@@ -267,10 +296,8 @@ static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, flo
   kp.out = ctx->d_knn.p;
   kp.two = 2;
   kp.prune_ratio = prune_ratio;
-  const int grid = std::min(bp.n_items, ctx->prop.multiProcessorCount);
-  knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(A.tmap_q, A.tmap_db, kp);
-  CU_CHECK(ctx, cudaGetLastError());
-  return MVGCUDA_OK;
+  kp.prune_rho = prune_rho;
+  return launch_knn_raw(ctx, A.tmap_q, A.tmap_db, kp);
 }
 
 constexpr long long kBatchRecords = 24ll << 20;  // queries per batch (384 MB of KnnRecord)
@@ -299,6 +326,102 @@ static int validate_pairs(mvgcuda_ctx* ctx, const Arena& A, int64_t n_pairs, con
   return MVGCUDA_OK;
 }
 
+// The admission factor actually used for a ratio: never below the ratio itself (a row with d < ratio * d(best) could be
+// a passing nearest neighbour and must always be admitted), 1 = plain best-distance bound, no rescans.
+static float effective_rho(const mvgcuda_ctx* ctx, float ratio_sq) {
+  float rho = ctx->prune_rho;
+  if (!(rho < 1.0f)) return 1.0f;
+  return std::min(1.0f, std::max(rho, ratio_sq * 1.002f));
+}
+
+// After the pruned K2 pass of a batch of nb pairs: find the ambiguous queries, match them again exactly (same kernel,
+// gathered query rows, prune_ratio = FLT_MAX) and put the exact records in place.  One small D2H + sync per batch; the
+// gathered rows go through a bounded buffer in as many rounds as needed.
+static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long n_records, float ratio_sq, float rho,
+                            int& launches) {
+  cudaStream_t st = ctx->stream;
+  CU_CHECK(ctx, ctx->d_resc_idx.reserve(std::max<long long>(n_records, 1)));
+  CU_CHECK(ctx, ctx->d_resc_cnt.reserve(nb));
+  CU_CHECK(ctx, ctx->h_resc_cnt.reserve(nb));
+  flag_ambiguous_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_jobs.p, ctx->d_knn.p, ratio_sq, rho, ctx->d_resc_idx.p,
+                                                        ctx->d_resc_cnt.p);
+  CU_CHECK(ctx, cudaGetLastError());
+  ++launches;
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_resc_cnt.p, ctx->d_resc_cnt.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(ctx, cudaStreamSynchronize(st));
+  long long total = 0;
+  for (int k = 0; k < nb; ++k) total += ctx->h_resc_cnt.p[k];
+  if (total == 0) return MVGCUDA_OK;
+  ctx->rescanned += total;
+  const int cap = (int)std::min<long long>(std::max(ctx->rescan_cap_rows, 1), round_up((int)std::min<long long>(total, 1 << 30), 256));
+  const size_t ccol_len = (size_t)(cap / kTileDb + 2) * kTileC;
+  CU_CHECK(ctx, ctx->d_resc_desc.reserve((size_t)(cap + kBlockQ) * kDim));
+  CU_CHECK(ctx, ctx->d_resc_ccol.reserve(ccol_len));
+  CU_CHECK(ctx, ctx->d_resc_knn.reserve(cap));
+  const int tm_rows = (int)(ctx->d_resc_desc.cap / kDim);
+  if (ctx->tmap_resc_base != ctx->d_resc_desc.p || ctx->tmap_resc_rows != tm_rows) {
+    int rc = make_tmap(ctx, &ctx->tmap_resc, ctx->d_resc_desc.p, tm_rows, kBlockQ);
+    if (rc) return rc;
+    ctx->tmap_resc_base = ctx->d_resc_desc.p;
+    ctx->tmap_resc_rows = tm_rows;
+  }
+  CU_CHECK(ctx, ctx->h_rjobs.reserve(nb + 1));
+  CU_CHECK(ctx, ctx->h_rsrc.reserve(nb + 1));
+  CU_CHECK(ctx, ctx->h_ritem_start.reserve(nb + 2));
+  CU_CHECK(ctx, ctx->d_rjobs.reserve(nb + 1));
+  CU_CHECK(ctx, ctx->d_rsrc.reserve(nb + 1));
+  CU_CHECK(ctx, ctx->d_ritem_start.reserve(nb + 2));
+  int j = 0, first = 0;
+  while (j < nb) {
+    int used = 0, n_rj = 0, items = 0;
+    while (j < nb && used < cap) {
+      const int left = ctx->h_resc_cnt.p[j] - first;
+      if (left <= 0) { ++j; first = 0; continue; }
+      const int take = std::min(left, cap - used);
+      const PairJob& J = ctx->h_jobs.p[j];
+      ctx->h_rsrc.p[n_rj] = RescanSrc{J.out_off, J.q_row0, first, take, used};
+      PairJob& R = ctx->h_rjobs.p[n_rj];
+      R = J;
+      R.q_row0 = used;
+      R.q_rows = take;
+      R.out_off = used;
+      R.valid = 1;
+      ctx->h_ritem_start.p[n_rj] = items;
+      items += (take + kBlockQ - 1) / kBlockQ;
+      ++n_rj;
+      used += take;
+      first += take;
+    }
+    if (n_rj == 0) break;
+    ctx->h_ritem_start.p[n_rj] = items;
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rjobs.p, ctx->h_rjobs.p, n_rj * sizeof(PairJob), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rsrc.p, ctx->h_rsrc.p, n_rj * sizeof(RescanSrc), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ritem_start.p, ctx->h_ritem_start.p, (n_rj + 1) * sizeof(int),
+                                  cudaMemcpyHostToDevice, st));
+    rescan_gather_kernel<<<n_rj, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, A.desc.p, A.ccol.p, ctx->d_resc_desc.p,
+                                               ctx->d_resc_ccol.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    KnnParams kp;
+    kp.ccol = A.ccol.p;
+    kp.qcol = ctx->d_resc_ccol.p;
+    kp.jobs = ctx->d_rjobs.p;
+    kp.item_start = ctx->d_ritem_start.p;
+    kp.n_jobs = n_rj;
+    kp.n_items = items;
+    kp.out = ctx->d_resc_knn.p;
+    kp.two = 2;
+    kp.prune_ratio = FLT_MAX;
+    kp.prune_rho = 1.0f;
+    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A.tmap_db, kp);
+    if (rc) return rc;
+    rescan_scatter_kernel<<<n_rj, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    launches += 3;
+    CU_CHECK(ctx, cudaStreamSynchronize(st));  // the pinned job lists are rewritten by the next round
+  }
+  return MVGCUDA_OK;
+}
+
 // Optional consumer of finished batches (collection level): `on_batch(p1)` is called as soon as the raw matches of
 // pairs [0, p1) are on the host, so that the host-side coordinate de-dup overlaps the GPU work of the next batch.
 // `results_mtx` is held exclusively while the pinned result buffer is re-allocated.
@@ -321,6 +444,7 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
   ctx->last_was_collection = false;
   float gpu_ms = 0.f, knn_ms = 0.f;
   int knn_launches = 0, launches = 0;
+  ctx->rescanned = 0;
   long long match_base = 0;
   cudaStream_t st = ctx->stream;
 
@@ -348,9 +472,15 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], st));
     // ratio <= 1: records only have to carry what the ratio test and the match list need (ratio-aware pruning);
     // ratio > 1 keeps the exact 2nd neighbour of every query for the tie fix-up below
-    rc = launch_knn(ctx, A, bp, (ratio_sq <= 1.0f) ? ratio_sq : FLT_MAX);
+    const bool prune = ratio_sq <= 1.0f;
+    const float rho = prune ? effective_rho(ctx, ratio_sq) : 1.0f;
+    rc = launch_knn(ctx, A, bp, prune ? ratio_sq : FLT_MAX, rho);
     if (rc) return rc;
-    CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (prune && rho < 1.0f && bp.n_items) {
+      rc = rescan_ambiguous(ctx, A, nb, bp.n_records, ratio_sq, rho, launches);
+      if (rc) return rc;
+    }
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], st));  // K2 incl. the exact second pass over ambiguous queries
     if (ratio_sq > 1.0f) {
       // For ratio > 1 a tie d1 == d2 passes the test, so WHICH of the tied rows is reported matters: reproduce the
       // reference's std::partial_sort choice exactly (one extra CUDA-core pass per pair; the usual ratios <= 1 skip it).
@@ -413,6 +543,7 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     out->knn_kernel_ms = knn_ms;
     out->knn_kernel_launches = knn_launches;
     out->total_launches = launches;
+    out->rescanned_queries = ctx->rescanned;
   }
   return MVGCUDA_OK;
 }
@@ -440,7 +571,7 @@ static int knn2_impl(mvgcuda_ctx* ctx, const Arena& A, int db_img, int q_img, in
   cudaStream_t st = ctx->stream;
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jobs.p, ctx->h_jobs.p, sizeof(PairJob), cudaMemcpyHostToDevice, st));
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_item_start.p, ctx->h_item_start.p, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
-  rc = launch_knn(ctx, A, bp, FLT_MAX);  // exact 2-NN of every query
+  rc = launch_knn(ctx, A, bp, FLT_MAX, 1.0f);  // exact 2-NN of every query
   if (rc) return rc;
   if (tie_mode == MVGCUDA_TIE_REFERENCE) {
     const int warps_per_block = 8;
@@ -601,10 +732,21 @@ void mvgcuda_destroy(mvgcuda_ctx* ctx) {
   ctx->d_npass.release(); ctx->d_counts.release(); ctx->d_offsets.release(); ctx->d_total.release();
   ctx->d_matches.release();
   ctx->h_jobs.release(); ctx->h_item_start.release(); ctx->h_total.release();
+  ctx->d_resc_idx.release(); ctx->d_resc_cnt.release(); ctx->d_resc_ccol.release(); ctx->d_ritem_start.release();
+  ctx->d_resc_desc.release(); ctx->d_resc_knn.release(); ctx->d_rjobs.release(); ctx->d_rsrc.release();
+  ctx->h_resc_cnt.release(); ctx->h_ritem_start.release(); ctx->h_rjobs.release(); ctx->h_rsrc.release();
   ctx->r_counts.release(); ctx->r_offsets.release(); ctx->r_matches.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+}
+
+int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows) {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (!(prune_rho > 0.0f) || prune_rho > 1.0f || rescan_rows < 0) { ctx->set_error("bad tuning values"); return MVGCUDA_ERR_INVALID; }
+  ctx->prune_rho = prune_rho;
+  ctx->rescan_cap_rows = rescan_rows ? rescan_rows : kDefaultRescanRows;
+  return MVGCUDA_OK;
 }
 
 int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream) {

@@ -41,6 +41,7 @@ class _PairMatches(C.Structure):
         ("knn_kernel_ms", C.c_float),
         ("knn_kernel_launches", C.c_int32),
         ("total_launches", C.c_int32),
+        ("rescanned_queries", C.c_int64),
     ]
 
 
@@ -68,6 +69,7 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_destroy": (None, [_ctx]),
     "mvgcuda_last_error": (C.c_char_p, [_ctx]),
     "mvgcuda_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "mvgcuda_set_tuning": (C.c_int, [_ctx, C.c_float, C.c_int]),
     "mvgcuda_upload_images": (C.c_int, [_ctx, C.c_int, _u8pp, _i32p, C.c_int]),
     "mvgcuda_num_images": (C.c_int, [_ctx]),
     "mvgcuda_image_rows": (C.c_int, [_ctx, C.c_int]),
@@ -183,6 +185,10 @@ class Context:
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._lib.mvgcuda_set_stream(self._h, C.c_void_p(cuda_stream)), "mvgcuda_set_stream")
 
+    def set_tuning(self, prune_rho: float = 0.8, rescan_rows: int = 0) -> None:
+        """Ratio-aware pruning knobs (results never depend on them): admission factor and rescan buffer rows."""
+        self._check(self._lib.mvgcuda_set_tuning(self._h, C.c_float(prune_rho), int(rescan_rows)), "mvgcuda_set_tuning")
+
     def device_info(self) -> dict:
         di = _DeviceInfo()
         self._check(self._lib.mvgcuda_get_device_info(self._h, C.byref(di)), "mvgcuda_get_device_info")
@@ -257,7 +263,7 @@ class Context:
         total = int(offsets[n])
         matches = (np.ctypeslib.as_array(pm.matches, shape=(max(total, 1) * 2,))[: total * 2].copy().reshape(total, 2))
         timing = {"gpu_ms": pm.gpu_ms, "knn_kernel_ms": pm.knn_kernel_ms, "knn_kernel_launches": pm.knn_kernel_launches,
-                  "total_launches": pm.total_launches}
+                  "total_launches": pm.total_launches, "rescanned_queries": pm.rescanned_queries}
         return PairMatches(pairs, counts, offsets, matches, timing)
 
     def match_pairs(self, pairs: np.ndarray, ratio_sq: float, collect: bool = True):

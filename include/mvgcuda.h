@@ -73,6 +73,12 @@ const char* mvgcuda_last_error(const mvgcuda_ctx* ctx);
  * NULL restores the context's own stream. */
 int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
 
+/* Tuning of the ratio-aware pruning of the pair / collection level (results never depend on it).
+ * prune_rho in (0, 1]: a query that currently fails the ratio test only admits db rows with d <= prune_rho * d(best);
+ * 1 = plain best-distance bound (no query is ever matched twice), default 0.8.  It is clamped from below to the ratio
+ * of the call.  rescan_rows: rows of the buffer the ambiguous queries are gathered into per round (0 = default 2^20). */
+int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows);
+
 /* ------------------------------------------------------------------------------------------
  * Residency: copy n_images descriptor arrays into the context's HBM arena (replaces the
  * map_descriptors residency of MatcherAllInMemory::LoadData, matcher_all_in_memory.h:44-60,
@@ -131,6 +137,8 @@ typedef struct mvgcuda_pair_matches {
   float knn_kernel_ms;
   int32_t knn_kernel_launches;
   int32_t total_launches;
+  /* queries whose pruned record could not decide the ratio test and were matched a second time, exactly */
+  int64_t rescanned_queries;
 } mvgcuda_pair_matches;
 
 int mvgcuda_match_pairs(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs, float ratio_sq,

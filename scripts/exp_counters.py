@@ -16,3 +16,4 @@ ctx.match_pairs(pairs, float(pkg.square_f32(0.8)), collect=False)
 fn(buf, 1)
 c = list(buf)
 print(f"chunks {c[0]}  slow chunks {c[1]} ({100*c[1]/c[0]:.1f}%)  group hits {c[2]} ({c[2]/max(c[1],1):.2f} per slow chunk)  lane hits {c[3]} ({c[3]/max(c[1],1):.2f} per slow chunk, {c[3]/(c[0]*32)*100:.2f}% of lane-chunks)")
+print(f"queries {c[4]}  tracked pass {c[5]} ({100*c[5]/max(c[4],1):.2f}%)  ambiguous (needs rescan) {c[6]} ({100*c[6]/max(c[4],1):.2f}% of queries)")

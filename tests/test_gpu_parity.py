@@ -156,8 +156,9 @@ def _row_at_distance(qrow: np.ndarray, d: int, rng) -> np.ndarray:
     return (qrow.astype(np.int16) + delta).astype(np.uint8)
 
 
+@pytest.mark.parametrize("rho,rescan_rows", [(0.8, 0), (1.0, 0), (0.65, 256)])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_ratio_aware_pruning_adversarial_orders(ctx, pkg, l1, seed):
+def test_ratio_aware_pruning_adversarial_orders(ctx, pkg, l1, seed, rho, rescan_rows):
     """Scan orders built to break an unsound pruning rule: per query a handful of near rows
     whose distances straddle the ratio threshold (e.g. 150, 200 early, then 130, then 90: the true pair (90, 130) fails
     at 0.8^2 although (90, 150) would pass), scattered over tiles and column halves among far filler rows."""
@@ -178,16 +179,44 @@ def test_ratio_aware_pruning_adversarial_orders(ctx, pkg, l1, seed):
         dbs.append(db)
     ctx.upload_images(dbs + [q])
     pairs = np.array([[i, len(dbs)] for i in range(len(dbs))], np.int32)
-    for r in (0.8, 0.6, 0.95, 1.0):
-        rs = float(pkg.square_f32(r))
-        res = ctx.match_pairs(pairs, rs)
-        n_pass = 0
-        for p, (i, j) in enumerate(pairs):
-            want = l1.pair_matches(dbs[i], q, rs)
-            assert np.array_equal(res.pair(p), want), f"ratio {r} db {i}"
-            n_pass += len(want)
-        if r in (0.8, 0.95):
-            assert 0 < n_pass < len(pairs) * (n_q - 1)                        # both outcomes occur
+    ctx.set_tuning(rho, rescan_rows)
+    try:
+        rescanned = 0
+        for r in (0.8, 0.6, 0.95, 1.0):
+            rs = float(pkg.square_f32(r))
+            res = ctx.match_pairs(pairs, rs)
+            rescanned += res.timing["rescanned_queries"]
+            n_pass = 0
+            for p, (i, j) in enumerate(pairs):
+                want = l1.pair_matches(dbs[i], q, rs)
+                assert np.array_equal(res.pair(p), want), f"ratio {r} db {i}"
+                n_pass += len(want)
+            if r in (0.8, 0.95):
+                assert 0 < n_pass < len(pairs) * (n_q - 1)                    # both outcomes occur
+        assert (rescanned == 0) if rho == 1.0 else (rescanned > 0)            # the exact second pass really ran
+    finally:
+        ctx.set_tuning()
+
+
+@pytest.mark.parametrize("rho,rescan_rows", [(0.8, 0), (0.65, 128), (0.9, 1000)])
+def test_rescan_of_ambiguous_queries_real_sift(ctx, pkg, l1, et, rho, rescan_rows):
+    """Real SIFT (data/et, 9 images, both directions of every pair): many queries sit in the ambiguous band, so the exact
+    second pass (gather -> same kernel -> scatter), its multi-round buffer and the splitting of a pair over rounds all
+    run; the matches must not depend on the tuning."""
+    descs, _ = et
+    ctx.upload_images(descs)
+    pairs = pkg.pairs_exhaustive(len(descs))
+    pairs = np.concatenate([pairs, pairs[:, ::-1]]).astype(np.int32)
+    ctx.set_tuning(rho, rescan_rows)
+    try:
+        for r in (0.6, 0.8):
+            rs = float(pkg.square_f32(r))
+            res = ctx.match_pairs(pairs, rs)
+            assert res.timing["rescanned_queries"] > 0
+            for p, (i, j) in enumerate(pairs):
+                assert np.array_equal(res.pair(p), l1.pair_matches(descs[i], descs[j], rs)), f"pair {i},{j} ratio {r}"
+    finally:
+        ctx.set_tuning()
 
 
 # ---------------------------------------------------------------- collection level + export (rows 7-14)
