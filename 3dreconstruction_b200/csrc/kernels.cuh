@@ -236,8 +236,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
             const KnnParams p) {
   extern __shared__ uint8_t smem_raw[];
   KnnSmem& s = *reinterpret_cast<KnnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+  // warp / lane through a shuffle: values ptxas cannot rematerialise.  Derived directly from %tid they are re-read with
+  // S2R (~25 clocks, and a dependent shift) inside the tile loop instead of being kept in a register.
+  const int lane = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x & 31), static_cast<int>(threadIdx.x & 31));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
 
 #if MVGCUDA_EXPERIMENT == 3
   if (threadIdx.x < 8) dbg_smem()[threadIdx.x] = 0;
@@ -346,11 +348,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       const uint32_t bound_saddr = ptx::smem_u32(&s.bound[item_it & 1][row]);
       // the other parity's slot is idle (every part left the previous item at the barrier below): reset it for the next item
       s.bound[(item_it & 1) ^ 1][row] = kTInit;
-      for (int t = 0; t < ntiles; ++t, ++acc_it, ++c_it) {
-        if ((acc_it & 1u) != par) continue;  // the other group's tile
-        const uint32_t sc = c_it % kSlotsC;
-        ptx::mbar_wait(&s.c_full[sc], (c_it / kSlotsC) & 1);
-        ptx::mbar_wait(&s.acc_full[par], (acc_it >> 1) & 1);
+      // this group's tiles of the item: running accumulator index of parity `par`
+      for (int t = static_cast<int>((par ^ acc_it) & 1u); t < ntiles; t += 2) {
+        const uint32_t acc = acc_it + t, cc_it = c_it + t;
+        const uint32_t sc = cc_it % kSlotsC;
+        ptx::mbar_wait(&s.c_full[sc], (cc_it / kSlotsC) & 1);
+        ptx::mbar_wait(&s.acc_full[par], (acc >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t cs = ptx::smem_u32(s.c[sc] + half * kPartCols);
         int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;
@@ -358,39 +361,42 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         const uint32_t cm_saddr = ptx::smem_u32(s.c[sc] + kTileDb + half * (kPartCols / kChunk));
         const int4 cm0 = ptx::lds128(cm_saddr);
         const int4 cm1 = ptx::lds128(cm_saddr + 16);
+        // Eight chunks of 16 columns through four register sets.  tcgen05.wait::ld waits for EVERY outstanding load, so
+        // each load is issued one chunk ahead of the wait that covers it: only the first wait of a tile sees the TMEM
+        // latency.  The accumulator goes back to the MMA warp as soon as the last chunk is in registers.
         int32_t v0[16], v1[16], v2[16], v3[16];
-        // first 64 columns
+#define MVG_CHUNK(v, k, cmv) epi_chunk16(v, cs + 64 * (k), cmv, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T)
         ptx::tmem_ld_32x32b_x16(taddr, v0);
         ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
         ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+        ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_wait_for(v2);
         ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
-        ptx::tmem_ld_wait_for(v0);
-        ptx::tmem_ld_wait_for(v1);
-        ptx::tmem_ld_wait_for(v2);
+        MVG_CHUNK(v0, 0, cm0.x);
         ptx::tmem_ld_wait_for(v3);
-        epi_chunk16(v0, cs, cm0.x, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 64, cm0.y, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 128, cm0.z, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 192, cm0.w, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        // second 64 columns; once they are in registers the accumulator goes back to the MMA warp
         ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
-        ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
-        ptx::tmem_ld_32x32b_x16(taddr + 96, v2);
-        ptx::tmem_ld_32x32b_x16(taddr + 112, v3);
+        MVG_CHUNK(v1, 1, cm0.y);
         ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        MVG_CHUNK(v2, 2, cm0.z);
         ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 96, v2);
+        MVG_CHUNK(v3, 3, cm0.w);
         ptx::tmem_ld_wait_for(v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 112, v3);
+        T = min(T, ptx::lds32_volatile(bound_saddr));
+        MVG_CHUNK(v0, 4, cm1.x);
         ptx::tmem_ld_wait_for(v3);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
+        MVG_CHUNK(v1, 5, cm1.y);
         T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v0, cs + 256, cm1.x, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v1, cs + 320, cm1.y, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        T = min(T, ptx::lds32_volatile(bound_saddr));
-        epi_chunk16(v2, cs + 384, cm1.z, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
-        epi_chunk16(v3, cs + 448, cm1.w, g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr, two, l1, l2, T);
+        MVG_CHUNK(v2, 6, cm1.z);
+        MVG_CHUNK(v3, 7, cm1.w);
+#undef MVG_CHUNK
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index.  Branch-free (selects):
@@ -409,6 +415,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
           g2i = n2i;
         }
       }
+      acc_it += ntiles;
+      c_it += ntiles;
       // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record
       if (part > 0) s.xchg[item_it & 1][part - 1][row] = make_int4(g1t, g1i, g2t, g2i);
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");  // the warps sharing these 32 queries
