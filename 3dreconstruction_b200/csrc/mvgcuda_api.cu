@@ -373,32 +373,41 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
   CU_CHECK(ctx, ctx->d_ritem_start.reserve(nb + 2));
   int j = 0, first = 0;
   while (j < nb) {
-    int used = 0, n_rj = 0, items = 0;
+    // n_rs gather/scatter sources (one per original pair with flagged queries); n_rj second-pass jobs: consecutive
+    // pairs against the same db image (the normal case, the pair list is (i, j)-ordered) share ONE job, so their few
+    // flagged queries fill 128-query blocks together instead of one nearly empty block per pair
+    int used = 0, n_rs = 0, n_rj = 0, items = 0;
     while (j < nb && used < cap) {
       const int left = ctx->h_resc_cnt.p[j] - first;
       if (left <= 0) { ++j; first = 0; continue; }
       const int take = std::min(left, cap - used);
       const PairJob& J = ctx->h_jobs.p[j];
-      ctx->h_rsrc.p[n_rj] = RescanSrc{J.out_off, J.q_row0, first, take, used};
-      PairJob& R = ctx->h_rjobs.p[n_rj];
-      R = J;
-      R.q_row0 = used;
-      R.q_rows = take;
-      R.out_off = used;
-      R.valid = 1;
-      ctx->h_ritem_start.p[n_rj] = items;
-      items += (take + kBlockQ - 1) / kBlockQ;
-      ++n_rj;
+      ctx->h_rsrc.p[n_rs++] = RescanSrc{J.out_off, J.q_row0, first, take, used};
+      if (n_rj > 0 && ctx->h_rjobs.p[n_rj - 1].db_row0 == J.db_row0 && ctx->h_rjobs.p[n_rj - 1].db_rows == J.db_rows) {
+        ctx->h_rjobs.p[n_rj - 1].q_rows += take;
+      } else {
+        PairJob& R = ctx->h_rjobs.p[n_rj];
+        R = J;
+        R.q_row0 = used;
+        R.q_rows = take;
+        R.out_off = used;
+        R.valid = 1;
+        ++n_rj;
+      }
       used += take;
       first += take;
+    }
+    for (int k = 0; k < n_rj; ++k) {
+      ctx->h_ritem_start.p[k] = items;
+      items += (ctx->h_rjobs.p[k].q_rows + kBlockQ - 1) / kBlockQ;
     }
     if (n_rj == 0) break;
     ctx->h_ritem_start.p[n_rj] = items;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rjobs.p, ctx->h_rjobs.p, n_rj * sizeof(PairJob), cudaMemcpyHostToDevice, st));
-    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rsrc.p, ctx->h_rsrc.p, n_rj * sizeof(RescanSrc), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rsrc.p, ctx->h_rsrc.p, n_rs * sizeof(RescanSrc), cudaMemcpyHostToDevice, st));
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ritem_start.p, ctx->h_ritem_start.p, (n_rj + 1) * sizeof(int),
                                   cudaMemcpyHostToDevice, st));
-    rescan_gather_kernel<<<n_rj, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, A.desc.p, A.ccol.p, ctx->d_resc_desc.p,
+    rescan_gather_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, A.desc.p, A.ccol.p, ctx->d_resc_desc.p,
                                                ctx->d_resc_ccol.p);
     CU_CHECK(ctx, cudaGetLastError());
     KnnParams kp;
@@ -414,7 +423,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     kp.prune_rho = 1.0f;
     int rc = launch_knn_raw(ctx, ctx->tmap_resc, A.tmap_db, kp);
     if (rc) return rc;
-    rescan_scatter_kernel<<<n_rj, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
+    rescan_scatter_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
     CU_CHECK(ctx, cudaGetLastError());
     launches += 3;
     CU_CHECK(ctx, cudaStreamSynchronize(st));  // the pinned job lists are rewritten by the next round
