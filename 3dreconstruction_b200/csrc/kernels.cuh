@@ -13,7 +13,7 @@
 #include "ptx.cuh"
 
 #ifndef MVGCUDA_EXPERIMENT
-#define MVGCUDA_EXPERIMENT 0  // developer probes only (see epi_chunk16); 0 = the product
+#define MVGCUDA_EXPERIMENT 0  // developer probes only (see epi_chunk16: 1 drain, 2/5/6/7 filter ladder, 3 counters); 0 = the product
 #endif
 #if MVGCUDA_EXPERIMENT == 3
 __device__ unsigned long long g_dbg[8];  // [0] chunks, [1] slow chunks, [2] group hits, [3] lane hits (chunk level)
@@ -156,35 +156,12 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
   return Pair2{min(a.lo, b.lo), __vimin3_s32(max(a.lo, b.lo), a.hi, b.hi)};
 }
 
-// One filter step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot products x = q.d:
-//   some row of the chunk can still enter the top-2  =>  min_norm(chunk) - 2*max(x) <= T   (T: best-known 2nd-smallest
-//   t = ||d||^2 - 2 q.d of this query, ties admitted).  10 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
-//   shared-memory traffic.  Only when some lane of the warp passes is the chunk examined in groups of 4, and only for the
-//   groups that pass are exact packed keys ((||d||^2 - 2x) << 8 | col, one IMAD each) formed and merged (top-2 of 4 by
-//   a small sorting network) into the tile's running top-2.
-// Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
-// by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
-__device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
-                                            const int g1t, const int g2t, const int qn, const float prune_ratio, const float prune_rho,
-                                            const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
-#if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
-  l1 = min(l1, x[0]);
-  return;
-#endif
-  int g[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
-  const int m = max(__vimax3_s32(g[0], g[1], g[2]), g[3]);
-#if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
-  l1 = min(l1, m + T + cmin);
-  return;
-#endif
-  DBG_ADD(0, 1);
-#if MVGCUDA_EXPERIMENT == 3
-  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, two * m + T >= cmin));  // all lanes vote, lane 0 records
-  DBG_ADD(3, dbg_lane_hits);
-#endif
-  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
+// The exact step of a chunk: which groups of 4 rows can still matter, exact packed keys for those, top-2 merge, and the
+// new bound (items 2-5 of DESIGN.md section 4).  g[k] = max of the raw dot products of group k.
+__device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const int* __restrict__ g, const uint32_t cs_saddr,
+                                            const int cmin, const int g1t, const int g2t, const int qn,
+                                            const float prune_ratio, const float prune_rho, const uint32_t bound_saddr,
+                                            const int two, int& l1, int& l2, int& T) {
     DBG_ADD(1, 1);
     // which groups of 4 rows can still matter (all four votes issued back to back)
     const bool h0 = __any_sync(0xffffffffu, two * g[0] + T >= cmin);
@@ -222,7 +199,62 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
     const int tf = __float2int_ru(__fmul_ru(prune_rho, __int2float_rn(qn + c1))) - qn;
     T = min(T, passes ? c2 : tf);
     ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
+}
+
+// One filter step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot products x = q.d:
+//   some row of the chunk can still enter the top-2  =>  min_norm(chunk) - 2*max(x) <= T   (T: best-known 2nd-smallest
+//   t = ||d||^2 - 2 q.d of this query, ties admitted).  10 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
+//   shared-memory traffic.  Only when some lane of the warp passes is the chunk examined in groups of 4, and only for the
+//   groups that pass are exact packed keys ((||d||^2 - 2x) << 8 | col, one IMAD each) formed and merged (top-2 of 4 by
+//   a small sorting network) into the tile's running top-2.
+// Exactness: the test is necessary for membership in the final top-2, so no candidate is ever lost; ties are decided
+// by the packed compare (same tile) and the strict merge (earlier tile wins), i.e. lowest db row.
+__device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
+                                            const int g1t, const int g2t, const int qn, const float prune_ratio, const float prune_rho,
+                                            const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
+#if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
+  l1 = min(l1, x[0]);
+  return;
+#endif
+  int g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
+  const int m = max(__vimax3_s32(g[0], g[1], g[2]), g[3]);
+#if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
+  l1 = min(l1, m + T + cmin);
+  return;
+#endif
+#if MVGCUDA_EXPERIMENT == 5  // fast path + vote, no branch (results wrong)
+  l1 = min(l1, __any_sync(0xffffffffu, two * m + T >= cmin) ? m : l1);
+  return;
+#endif
+#if MVGCUDA_EXPERIMENT == 6  // fast path + vote + branch to a trivial exact step (results wrong)
+  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
+    l1 = min(l1, m);
+    T = min(T, l1);
+    ptx::red_min_shared(bound_saddr, T);
   }
+  return;
+#endif
+  DBG_ADD(0, 1);
+#if MVGCUDA_EXPERIMENT == 3
+  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, two * m + T >= cmin));  // all lanes vote, lane 0 records
+  DBG_ADD(3, dbg_lane_hits);
+#endif
+#if MVGCUDA_EXPERIMENT == 7  // the real exact step compiled in but never taken (static cost probe; results wrong)
+  if (__any_sync(0xffffffffu, two * m + T >= cmin) && two == 3) {
+#else
+  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
+#endif
+    epi_exact16(x, g, cs_saddr, cmin, g1t, g2t, qn, prune_ratio, prune_rho, bound_saddr, two, l1, l2, T);
+  }
+}
+
+// max of 16 in 8 three-input ops
+__device__ __forceinline__ int max16(const int32_t* __restrict__ x) {
+  const int a = __vimax3_s32(__vimax3_s32(x[0], x[1], x[2]), __vimax3_s32(x[3], x[4], x[5]), __vimax3_s32(x[6], x[7], x[8]));
+  const int b = __vimax3_s32(__vimax3_s32(x[9], x[10], x[11]), __vimax3_s32(x[12], x[13], x[14]), x[15]);
+  return max(a, b);
 }
 
 constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overflow and passes every chunk
@@ -230,6 +262,13 @@ constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overf
 // (t, index) lexicographic order: smaller distance first, lower db row on ties
 __device__ __forceinline__ bool cand_less(int ta, int ia, int tb, int ib) { return ta < tb || (ta == tb && ia < ib); }
 
+// kDeferred selects the epilogue schedule of a tile (both are bit-identical in their results):
+//   false  in place: each chunk is filtered and, if needed, examined exactly while it sits in registers; the TMEM loads
+//          rotate through four register sets.  Best up to ~10-20k db rows.
+//   true   filter first: all eight chunks are reduced to their maxima, the few that still matter are loaded a second
+//          time for the exact step (one rolled copy).  First tiles of an item cost more (every chunk matters and is
+//          loaded twice), later tiles less: +10 % at 40k rows, -10 % at 2k rows, equal at 10k (profiles/r01l_*).
+template <bool kDeferred>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 B
             const __grid_constant__ CUtensorMap tmap_db,  // box 256 rows x 128 B
@@ -361,6 +400,57 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         const uint32_t cm_saddr = ptx::smem_u32(s.c[sc] + kTileDb + half * (kPartCols / kChunk));
         const int4 cm0 = ptx::lds128(cm_saddr);
         const int4 cm1 = ptx::lds128(cm_saddr + 16);
+        if constexpr (kDeferred && MVGCUDA_EXPERIMENT == 0) {
+        // Filter first, exact step later (the variant launched for long scans, see launch_knn_raw).  The filter needs only the maximum of a chunk, so the 16 registers of a chunk
+        // are dead eight max ops after they arrive and the whole 128-column slice drains in two batches of four loads.
+        // Per lane one bit per chunk records "some row of this chunk may still matter" (bound as of the tile start:
+        // conservative, the bound only shrinks); the OR over the warp (one REDUX) says which chunks need the exact
+        // step.  Those few (3 % of the chunks) are loaded from TMEM a second time, one after the other, by ONE rolled
+        // copy of the exact step -- the accumulator is only handed back after that.
+        int32_t v0[16], v1[16], v2[16], v3[16];
+        uint32_t hits = 0;
+        ptx::tmem_ld_32x32b_x16(taddr, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
+        ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_wait_for(v2);
+        ptx::tmem_ld_wait_for(v3);
+        hits |= (two * max16(v0) + T >= cm0.x) ? 1u : 0u;
+        hits |= (two * max16(v1) + T >= cm0.y) ? 2u : 0u;
+        hits |= (two * max16(v2) + T >= cm0.z) ? 4u : 0u;
+        hits |= (two * max16(v3) + T >= cm0.w) ? 8u : 0u;
+        ptx::tmem_ld_32x32b_x16(taddr + 64, v0);
+        ptx::tmem_ld_32x32b_x16(taddr + 80, v1);
+        ptx::tmem_ld_32x32b_x16(taddr + 96, v2);
+        ptx::tmem_ld_32x32b_x16(taddr + 112, v3);
+        ptx::tmem_ld_wait_for(v0);
+        ptx::tmem_ld_wait_for(v1);
+        ptx::tmem_ld_wait_for(v2);
+        ptx::tmem_ld_wait_for(v3);
+        hits |= (two * max16(v0) + T >= cm1.x) ? 16u : 0u;
+        hits |= (two * max16(v1) + T >= cm1.y) ? 32u : 0u;
+        hits |= (two * max16(v2) + T >= cm1.z) ? 64u : 0u;
+        hits |= (two * max16(v3) + T >= cm1.w) ? 128u : 0u;
+        uint32_t todo = __reduce_or_sync(0xffffffffu, hits);
+#pragma unroll 1
+        while (todo) {
+          const int k = __ffs(todo) - 1;
+          todo &= todo - 1;
+          ptx::tmem_ld_32x32b_x16(taddr + 16 * k, v0);
+          ptx::tmem_ld_wait_for(v0);
+          int g[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) g[q4] = max(__vimax3_s32(v0[4 * q4], v0[4 * q4 + 1], v0[4 * q4 + 2]), v0[4 * q4 + 3]);
+          T = min(T, ptx::lds32_volatile(bound_saddr));
+          epi_exact16(v0, g, cs + 64 * k, ptx::lds32(cm_saddr + 4 * k), g1t, g2t, qn, p.prune_ratio, p.prune_rho, bound_saddr,
+                      two, l1, l2, T);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
+        } else {
         // Eight chunks of 16 columns through four register sets.  tcgen05.wait::ld waits for EVERY outstanding load, so
         // each load is issued one chunk ahead of the wait that covers it: only the first wait of a tile sees the TMEM
         // latency.  The accumulator goes back to the MMA warp as soon as the last chunk is in registers.
@@ -397,6 +487,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         MVG_CHUNK(v2, 6, cm1.z);
         MVG_CHUNK(v3, 7, cm1.w);
 #undef MVG_CHUNK
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&s.c_empty[sc]);
         // merge the tile's top-2 into the running top-2; ties keep the earlier (lower) index.  Branch-free (selects):

@@ -141,6 +141,7 @@ struct mvgcuda_ctx {
   const uint8_t* tmap_resc_base = nullptr;
   int tmap_resc_rows = 0;
   long long rescanned = 0;  // queries matched a second time by the last match call
+  int force_epilogue = -1;  // -1 auto (by db size), 0 in place, 1 filter first; env MVGCUDA_EPILOGUE, for tests
   PinnedBuf<long long> h_total;
 
   // results of the last match call
@@ -251,12 +252,13 @@ struct BatchPlan {
   int n_jobs = 0;
   int n_items = 0;
   long long n_records = 0;
+  long long mean_db_rows = 0;  // item-weighted mean db rows of the batch
 };
 
 // Fill h_jobs / h_item_start for pairs [p0, p1) of the list; images from arena A.
 static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, int64_t p0, int64_t p1, BatchPlan& bp) {
   bp.n_jobs = (int)(p1 - p0);
-  long long rec = 0;
+  long long rec = 0, db_sum = 0;
   int items = 0;
   for (int64_t p = p0; p < p1; ++p) {
     const int I = pairs[2 * p], J = pairs[2 * p + 1];
@@ -268,18 +270,29 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
     j.out_off = (int)rec;
     j.valid = (j.db_rows >= 2 && j.q_rows >= 1) ? 1 : 0;
     ctx->h_item_start.p[p - p0] = items;
-    if (j.valid) items += (j.q_rows + kBlockQ - 1) / kBlockQ;
+    if (j.valid) {
+      const int ni = (j.q_rows + kBlockQ - 1) / kBlockQ;
+      items += ni;
+      db_sum += (long long)ni * j.db_rows;
+    }
     rec += j.q_rows;
   }
+  bp.mean_db_rows = items ? db_sum / items : 0;
   ctx->h_item_start.p[p1 - p0] = items;
   bp.n_items = items;
   bp.n_records = rec;
 }
 
-static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp) {
+// `deferred`: the filter-first epilogue schedule, which pays off for long scans (see knn2_kernel).
+constexpr int kDeferredMinDbRows = 20000;
+static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp,
+                          bool deferred) {
   if (kp.n_items == 0) return MVGCUDA_OK;
   const int grid = std::min(kp.n_items, ctx->prop.multiProcessorCount);
-  knn2_kernel<<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
+  if (deferred)
+    knn2_kernel<true><<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
+  else
+    knn2_kernel<false><<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
   CU_CHECK(ctx, cudaGetLastError());
   return MVGCUDA_OK;
 }
@@ -297,7 +310,8 @@ static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, flo
   kp.two = 2;
   kp.prune_ratio = prune_ratio;
   kp.prune_rho = prune_rho;
-  return launch_knn_raw(ctx, A.tmap_q, A.tmap_db, kp);
+  const bool deferred = ctx->force_epilogue >= 0 ? ctx->force_epilogue != 0 : bp.mean_db_rows >= kDeferredMinDbRows;
+  return launch_knn_raw(ctx, A.tmap_q, A.tmap_db, kp, deferred);
 }
 
 constexpr long long kBatchRecords = 24ll << 20;  // queries per batch (384 MB of KnnRecord)
@@ -421,7 +435,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     kp.two = 2;
     kp.prune_ratio = FLT_MAX;
     kp.prune_rho = 1.0f;
-    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A.tmap_db, kp);
+    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A.tmap_db, kp, ctx->force_epilogue > 0);
     if (rc) return rc;
     rescan_scatter_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
     CU_CHECK(ctx, cudaGetLastError());
@@ -722,11 +736,17 @@ int mvgcuda_create(int device, mvgcuda_ctx** out) {
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
   ctx->knn_smem = sizeof(KnnSmem) + 1024;
-  if ((e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
-    return fail("cudaFuncSetAttribute(knn2_kernel)", e);
+  if ((e = cudaFuncSetAttribute(knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(knn2_kernel<false>)", e);
+  if ((e = cudaFuncSetAttribute(knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(knn2_kernel<true>)", e);
   if ((e = cudaFuncSetAttribute(i8_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kBytesA + kBytesB + 1024))) != cudaSuccess)
     return fail("cudaFuncSetAttribute(probe)", e);
+  if (const char* ep = getenv("MVGCUDA_EPILOGUE")) {  // test knob: force one epilogue schedule (results never differ)
+    if (!strcmp(ep, "deferred")) ctx->force_epilogue = 1;
+    else if (!strcmp(ep, "inplace")) ctx->force_epilogue = 0;
+  }
   *out = ctx;
   return MVGCUDA_OK;
 }

@@ -78,6 +78,9 @@ int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
  * 1 = plain best-distance bound (no query is ever matched twice), default 0.8.  It is clamped from below to the ratio
  * of the call.  rescan_rows: rows of the buffer the ambiguous queries are gathered into per round (0 = default 2^20). */
 int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows);
+/* The kernel has two epilogue schedules with identical results ("inplace", "deferred"); the library picks one per batch
+ * from the db image size.  Environment variable MVGCUDA_EPILOGUE=inplace|deferred (read by mvgcuda_create) forces one;
+ * the parity tests run under both. */
 
 /* ------------------------------------------------------------------------------------------
  * Residency: copy n_images descriptor arrays into the context's HBM arena (replaces the
