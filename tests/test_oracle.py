@@ -174,6 +174,46 @@ def test_l1_vs_l0_random(l1, l0):
             assert np.array_equal(l0.pair_matches(db, q, rs), l1.pair_matches(db, q, rs))
 
 
+def test_l1_vs_l0_ratio_borderline_clusters(l1, l0, pkg):
+    """The inputs the GPU pruning tests lean on (near-duplicate clusters whose d1/d2 straddles the ratio threshold, and
+    hand-placed rows at chosen distances): the restatement must agree with the REFERENCE's own code on them, so that
+    'GPU == L1' on these sets means 'GPU == reference'."""
+    synth = pkg.synth
+    rng = np.random.default_rng(77)
+    for trial in range(4):
+        n_db, n_q = int(rng.integers(300, 900)), int(rng.integers(100, 400))
+        base = synth.image(700 + trial, 0, max(2, n_db // 4), np.zeros((0, 128), np.uint8), shared=0.0)
+        src = rng.integers(0, len(base), n_db)
+        amp = rng.integers(0, 40, (n_db, 1))
+        db = np.clip(base[src].astype(np.int16) + rng.integers(-1, 2, (n_db, 128)) * amp, 0, 255).astype(np.uint8)
+        qs = rng.integers(0, len(base), n_q)
+        q = np.clip(base[qs].astype(np.int16) + rng.integers(-1, 2, (n_q, 128)) * rng.integers(0, 12, (n_q, 1)), 0, 255).astype(np.uint8)
+        n_pass = 0
+        for r in (0.6, 0.8, 0.95, 1.0):
+            rs = float(l0.square(r))
+            want = l0.pair_matches(db, q, rs)
+            assert np.array_equal(want, l1.pair_matches(db, q, rs))
+            n_pass += len(want)
+        assert 0 < n_pass < 4 * (n_q - 1)
+    # rows at exact distances 150, 200, 130, 90 from a flat query, in that scan order: (90, 130) fails at 0.8^2
+    q = np.full((2, 128), 50, np.uint8)
+    db = rng.integers(150, 256, (40, 128), dtype=np.uint8)
+    for slot, d in zip((3, 9, 21, 33), (150, 200, 130, 90)):
+        row = q[0].astype(np.int16).copy()
+        k = 0
+        while d > 0:
+            v = min(11, int(np.sqrt(d)))
+            row[k] += v
+            d -= v * v
+            k += 1
+        db[slot] = row.astype(np.uint8)
+    rs = float(l0.square(0.8))
+    i0, d0 = l0.knn(db, q, 2)
+    assert list(d0[0].astype(int)) == [90, 130] and list(i0[0]) == [33, 21]
+    assert np.array_equal(l0.pair_matches(db, q, rs), l1.pair_matches(db, q, rs))
+    assert not (np.float32(90) < np.float32(rs) * np.float32(130))             # the pair fails the reference's test
+
+
 def test_l1_vs_l0_dedups(l1, l0):
     rng = np.random.default_rng(6)
     for trial in range(200):
