@@ -156,6 +156,13 @@ __device__ __forceinline__ Pair2 merge2(Pair2 a, Pair2 b) {
   return Pair2{min(a.lo, b.lo), __vimin3_s32(max(a.lo, b.lo), a.hi, b.hi)};
 }
 
+// max of 16 in 8 three-input ops
+__device__ __forceinline__ int max16(const int32_t* __restrict__ x) {
+  const int a = __vimax3_s32(__vimax3_s32(x[0], x[1], x[2]), __vimax3_s32(x[3], x[4], x[5]), __vimax3_s32(x[6], x[7], x[8]));
+  const int b = __vimax3_s32(__vimax3_s32(x[9], x[10], x[11]), __vimax3_s32(x[12], x[13], x[14]), x[15]);
+  return max(a, b);
+}
+
 // The exact step of a chunk: which groups of 4 rows can still matter, exact packed keys for those, top-2 merge, and the
 // new bound (items 2-5 of DESIGN.md section 4).  g[k] = max of the raw dot products of group k.
 __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const int* __restrict__ g, const uint32_t cs_saddr,
@@ -203,7 +210,7 @@ __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const
 
 // One filter step over a chunk of 16 db rows (TMEM columns), entirely on the raw dot products x = q.d:
 //   some row of the chunk can still enter the top-2  =>  min_norm(chunk) - 2*max(x) <= T   (T: best-known 2nd-smallest
-//   t = ||d||^2 - 2 q.d of this query, ties admitted).  10 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
+//   t = ||d||^2 - 2 q.d of this query, ties admitted).  8 max ops + 1 add + 1 compare + 1 vote per 16 rows and no
 //   shared-memory traffic.  Only when some lane of the warp passes is the chunk examined in groups of 4, and only for the
 //   groups that pass are exact packed keys ((||d||^2 - 2x) << 8 | col, one IMAD each) formed and merged (top-2 of 4 by
 //   a small sorting network) into the tile's running top-2.
@@ -216,10 +223,7 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
   l1 = min(l1, x[0]);
   return;
 #endif
-  int g[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
-  const int m = max(__vimax3_s32(g[0], g[1], g[2]), g[3]);
+  const int m = max16(x);  // 8 ops; the per-group maxima are only formed when the chunk goes to the exact step
 #if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
   l1 = min(l1, m + T + cmin);
   return;
@@ -246,15 +250,11 @@ __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const
 #else
   if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
 #endif
+    int g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
     epi_exact16(x, g, cs_saddr, cmin, g1t, g2t, qn, prune_ratio, prune_rho, bound_saddr, two, l1, l2, T);
   }
-}
-
-// max of 16 in 8 three-input ops
-__device__ __forceinline__ int max16(const int32_t* __restrict__ x) {
-  const int a = __vimax3_s32(__vimax3_s32(x[0], x[1], x[2]), __vimax3_s32(x[3], x[4], x[5]), __vimax3_s32(x[6], x[7], x[8]));
-  const int b = __vimax3_s32(__vimax3_s32(x[9], x[10], x[11]), __vimax3_s32(x[12], x[13], x[14]), x[15]);
-  return max(a, b);
 }
 
 constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overflow and passes every chunk
