@@ -823,6 +823,46 @@ int mvgcuda_match_pairs(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs,
   return match_pairs_impl(ctx, n_pairs, pairs, ratio_sq, out);
 }
 
+int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src) {
+  if (!ctx || !src || ctx == src) return MVGCUDA_ERR_INVALID;
+  const Arena& S = src->images;
+  Arena& A = ctx->images;
+  if (S.arena_rows <= 0 || !S.desc.p) { ctx->set_error("clone_images: the source context holds no images"); return MVGCUDA_ERR_INVALID; }
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (ctx->device != src->device) {
+    int can = 0;
+    CU_CHECK(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, src->device));
+    if (can) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);  // direct NVLink path; without it the copy is staged
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_CHECK(ctx, e);
+      (void)cudaGetLastError();
+    }
+  }
+  ctx->feats = src->feats;
+  ctx->r_pairs = 0;
+  A.row0 = S.row0;
+  A.rows = S.rows;
+  A.arena_rows = S.arena_rows;
+  const int n_images = (int)A.rows.size();
+  const size_t ccol_len = (size_t)(A.arena_rows / kTileDb) * kTileC;
+  CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
+  CU_CHECK(ctx, A.ccol.reserve(ccol_len));
+  CU_CHECK(ctx, A.img_row0.reserve(n_images + 1));
+  CU_CHECK(ctx, A.img_rows.reserve(std::max(n_images, 1)));
+  cudaStream_t st = ctx->stream;
+  CU_CHECK(ctx, cudaMemcpyPeerAsync(A.desc.p, ctx->device, S.desc.p, src->device, (size_t)A.arena_rows * kDim, st));
+  CU_CHECK(ctx, cudaMemcpyPeerAsync(A.ccol.p, ctx->device, S.ccol.p, src->device, ccol_len * sizeof(int), st));
+  CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_images)
+    CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
+  if (rc) return rc;
+  CU_CHECK(ctx, cudaStreamSynchronize(st));
+  return MVGCUDA_OK;
+}
+
 int mvgcuda_set_features(mvgcuda_ctx* ctx, int n_images, const float* const* feats_xy, const int32_t* rows) {
   if (!ctx) return MVGCUDA_ERR_INVALID;
   if (n_images != (int)ctx->images.rows.size()) { ctx->set_error("set_features: image count differs from uploaded set"); return MVGCUDA_ERR_INVALID; }

@@ -71,6 +71,7 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "mvgcuda_set_tuning": (C.c_int, [_ctx, C.c_float, C.c_int]),
     "mvgcuda_upload_images": (C.c_int, [_ctx, C.c_int, _u8pp, _i32p, C.c_int]),
+    "mvgcuda_clone_images": (C.c_int, [_ctx, _ctx]),
     "mvgcuda_num_images": (C.c_int, [_ctx]),
     "mvgcuda_image_rows": (C.c_int, [_ctx, C.c_int]),
     "mvgcuda_knn2": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _f32p]),
@@ -224,6 +225,10 @@ class Context:
             rws[k] = int(rows[k])
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rws, 0), "mvgcuda_upload_images")
         self._rows = [int(r) for r in rows]
+
+    def clone_images_from(self, src: "Context") -> None:
+        """Replica of another context's uploaded collection (and features), copied device to device."""
+        self._check(self._lib.mvgcuda_clone_images(self._h, src._h), "mvgcuda_clone_images")
 
     def set_features(self, feats_xy: Sequence[np.ndarray]) -> None:
         mats = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy]

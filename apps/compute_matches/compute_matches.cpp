@@ -15,6 +15,7 @@
 // Out of scope of this build: SIFT extraction (the stage before: .feat/.desc must exist) and
 // the AC-RANSAC geometric filter (the stage after: run the reference's own binary on the exported file).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +122,14 @@ bool load_feat_xy(const std::string& path, std::vector<float>& xy) {
   return !f.bad();
 }
 
+// decimal text of a non-negative integer, appended to a buffer (the export is hundreds of MB of small integers)
+inline void append_uint(std::string& out, unsigned long long v) {
+  char tmp[24];
+  int n = 0;
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) out.push_back(tmp[--n]);
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -165,20 +174,41 @@ int main(int argc, char** argv) {
   std::vector<std::vector<float> > xy(n);
   std::vector<int32_t> rows(n, 0);
   auto t0 = std::chrono::steady_clock::now();
-  for (int i = 0; i < n; ++i) {
-    const std::string base = opt.outdir + "/" + basename_part(names[i]);
-    if (!file_exists(base + ".feat") || !file_exists(base + ".desc")) {
+  {
+    // one image per task over the host cores: the .feat text parse dominates (4 floats per feature)
+    std::atomic<int> next(0), first_missing(n), first_bad(n);
+    auto load = [&]() {
+      for (int i = next++; i < n; i = next++) {
+        const std::string base = opt.outdir + "/" + basename_part(names[i]);
+        if (!file_exists(base + ".feat") || !file_exists(base + ".desc")) {
+          int cur = first_missing.load();
+          while (i < cur && !first_missing.compare_exchange_weak(cur, i)) {}
+          continue;
+        }
+        int drows = 0;
+        if (!load_desc(base + ".desc", desc[i], drows) || !load_feat_xy(base + ".feat", xy[i])) {
+          int cur = first_bad.load();
+          while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
+          continue;
+        }
+        rows[i] = (int32_t)std::min<size_t>(xy[i].size() / 2, (size_t)drows);  // row count from the features (matcher_all_in_memory.h:80)
+        xy[i].resize(2 * (size_t)rows[i]);
+      }
+    };
+    const int n_threads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::max(n, 1)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(load);
+    for (auto& t : pool) t.join();
+    if (first_missing.load() < n) {
+      const std::string base = opt.outdir + "/" + basename_part(names[first_missing.load()]);
       std::cerr << "missing " << base << ".feat/.desc: SIFT extraction (compute_matches.cpp:188-216) is outside this build; "
                 << "run the reference's extraction stage first" << std::endl;
       return EXIT_FAILURE;
     }
-    int drows = 0;
-    if (!load_desc(base + ".desc", desc[i], drows) || !load_feat_xy(base + ".feat", xy[i])) {
-      std::cerr << "cannot parse " << base << ".feat/.desc" << std::endl;
+    if (first_bad.load() < n) {
+      std::cerr << "cannot parse " << opt.outdir << "/" << basename_part(names[first_bad.load()]) << ".feat/.desc" << std::endl;
       return EXIT_FAILURE;
     }
-    rows[i] = (int32_t)std::min<size_t>(xy[i].size() / 2, (size_t)drows);  // row count from the features (matcher_all_in_memory.h:80)
-    xy[i].resize(2 * (size_t)rows[i]);
   }
   std::vector<int32_t> pairs;
   for (int i = 0; i < n; ++i)
@@ -207,26 +237,40 @@ int main(int argc, char** argv) {
   struct Shard { std::vector<int32_t> counts; std::vector<int32_t> matches; std::string error; float gpu_ms = 0; };
   std::vector<Shard> shards(gpus);
   auto t1 = std::chrono::steady_clock::now();
+  // GPU 0 reads the collection over PCIe once; every other GPU takes a replica of its arena device to device
+  // (NVLink / NVSwitch), then all match their shard of the pair list concurrently -- no collective afterwards
+  std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
+  auto destroy_all = [&]() { for (mvgcuda_ctx* c : ctxs) if (c) mvgcuda_destroy(c); };
+  if (mvgcuda_create(0, &ctxs[0]) != MVGCUDA_OK) { std::cerr << "GPU 0: " << mvgcuda_last_error(NULL) << std::endl; return EXIT_FAILURE; }
+  if (mvgcuda_upload_images(ctxs[0], n, dptr.data(), rows.data(), 0) != MVGCUDA_OK ||
+      mvgcuda_set_features(ctxs[0], n, fptr.data(), rows.data()) != MVGCUDA_OK) {
+    std::cerr << "GPU 0: " << mvgcuda_last_error(ctxs[0]) << std::endl;
+    destroy_all();
+    return EXIT_FAILURE;
+  }
   auto work = [&](int g) {
     Shard& S = shards[g];
-    mvgcuda_ctx* ctx = NULL;
-    if (mvgcuda_create(g, &ctx) != MVGCUDA_OK) { S.error = mvgcuda_last_error(NULL); return; }
+    if (g > 0) {
+      if (mvgcuda_create(g, &ctxs[g]) != MVGCUDA_OK) { S.error = mvgcuda_last_error(NULL); return; }
+      if (mvgcuda_clone_images(ctxs[g], ctxs[0]) != MVGCUDA_OK) { S.error = mvgcuda_last_error(ctxs[g]); return; }
+    }
+    mvgcuda_ctx* ctx = ctxs[g];
     const int64_t b = bounds[g], e = bounds[g + 1];
     mvgcuda_pair_matches pm;
-    if (mvgcuda_upload_images(ctx, n, dptr.data(), rows.data(), 0) != MVGCUDA_OK ||
-        mvgcuda_set_features(ctx, n, fptr.data(), rows.data()) != MVGCUDA_OK ||
-        mvgcuda_match_collection(ctx, e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
+    if (mvgcuda_match_collection(ctx, e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
       S.error = mvgcuda_last_error(ctx);
     } else {
       S.counts.assign(pm.counts, pm.counts + (e - b));
       S.matches.assign(pm.matches, pm.matches + 2 * pm.offsets[e - b]);
       S.gpu_ms = pm.gpu_ms;
     }
-    mvgcuda_destroy(ctx);
   };
-  std::vector<std::thread> th;
-  for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
-  for (auto& t : th) t.join();
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
+    for (auto& t : th) t.join();
+  }
+  destroy_all();  // only after every replica has been taken
   auto t2 = std::chrono::steady_clock::now();
   for (int g = 0; g < gpus; ++g)
     if (!shards[g].error.empty()) { std::cerr << "GPU " << g << ": " << shards[g].error << std::endl; return EXIT_FAILURE; }
@@ -234,21 +278,36 @@ int main(int argc, char** argv) {
   // export: pairs are generated in lexicographic (i,j) order == std::map iteration order
   FILE* f = fopen(putative.c_str(), "wb");
   if (!f) { std::cerr << "cannot write " << putative << std::endl; return EXIT_FAILURE; }
-  std::string buf;
-  char line[64];
   long long total = 0;
-  for (int g = 0; g < gpus; ++g) {
-    const Shard& S = shards[g];
-    size_t off = 0;
-    for (int64_t p = bounds[g]; p < bounds[g + 1]; ++p) {
-      const int c = S.counts[p - bounds[g]];
-      buf.append(line, snprintf(line, sizeof line, "%d %d\n%d\n", pairs[2 * p], pairs[2 * p + 1], c));
-      for (int k = 0; k < c; ++k, ++off) buf.append(line, snprintf(line, sizeof line, "%d %d\n", S.matches[2 * off], S.matches[2 * off + 1]));
-      total += c;
-      if (buf.size() > (1u << 20)) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+  {
+    // text of every shard formatted concurrently, written in shard (== pair) order
+    std::vector<std::string> text(gpus);
+    std::vector<long long> shard_total(gpus, 0);
+    auto format = [&](int g) {
+      const Shard& S = shards[g];
+      std::string& out = text[g];
+      out.reserve(S.matches.size() * 6 + (size_t)(bounds[g + 1] - bounds[g]) * 16 + 64);
+      size_t off = 0;
+      for (int64_t p = bounds[g]; p < bounds[g + 1]; ++p) {
+        const int c = S.counts[p - bounds[g]];
+        append_uint(out, (unsigned)pairs[2 * p]); out.push_back(' ');
+        append_uint(out, (unsigned)pairs[2 * p + 1]); out.push_back('\n');
+        append_uint(out, (unsigned)c); out.push_back('\n');
+        for (int k = 0; k < c; ++k, ++off) {
+          append_uint(out, (unsigned)S.matches[2 * off]); out.push_back(' ');
+          append_uint(out, (unsigned)S.matches[2 * off + 1]); out.push_back('\n');
+        }
+        shard_total[g] += c;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; ++g) th.emplace_back(format, g);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < gpus; ++g) {
+      fwrite(text[g].data(), 1, text[g].size(), f);
+      total += shard_total[g];
     }
   }
-  fwrite(buf.data(), 1, buf.size(), f);
   if (fclose(f) != 0) { std::cerr << "short write to " << putative << std::endl; return EXIT_FAILURE; }
   auto t3 = std::chrono::steady_clock::now();
   auto ms = [](std::chrono::steady_clock::time_point a_, std::chrono::steady_clock::time_point b_) {

@@ -93,6 +93,11 @@ int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows);
  * `pinned` != 0 promises that host buffers are page-locked (async H2D). */
 int mvgcuda_upload_images(mvgcuda_ctx* ctx, int n_images, const uint8_t* const* desc,
                           const int32_t* rows, int pinned);
+/* Replica for another GPU of the box: copy the arena of `src` (descriptors, per-row constants, and the features if they
+ * were set) into `ctx` device-to-device -- over NVLink / NVSwitch when the two GPUs are peers -- instead of reading the
+ * collection over PCIe once per GPU.  `src` must have finished its upload and must not upload or be destroyed meanwhile;
+ * it may be matching.  Replaces any image set of `ctx`. */
+int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src);
 int mvgcuda_num_images(const mvgcuda_ctx* ctx);
 int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image); /* <0 on bad id */
 

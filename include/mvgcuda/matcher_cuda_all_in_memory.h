@@ -86,16 +86,24 @@ class MatcherCudaAllInMemory : public Matcher {
     }
     std::vector<std::vector<std::vector<IndexedMatch> > > shard_out(gpus);
     std::vector<std::string> errors(gpus);
+    // GPU 0 reads the collection over PCIe; the other GPUs take a replica of its arena device to device (NVLink)
+    std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
+    if (mvgcuda_create(0, &ctxs[0]) != MVGCUDA_OK) {
+      errors[0] = mvgcuda_last_error(NULL);
+    } else if (mvgcuda_upload_images(ctxs[0], n, desc.data(), rows.data(), 0) != MVGCUDA_OK ||
+               mvgcuda_set_features(ctxs[0], n, xy.data(), rows.data()) != MVGCUDA_OK) {
+      errors[0] = mvgcuda_last_error(ctxs[0]);
+    }
     auto work = [&](int g) {
-      mvgcuda_ctx* ctx = NULL;
-      if (mvgcuda_create(g, &ctx) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(NULL); return; }
+      if (g > 0) {
+        if (mvgcuda_create(g, &ctxs[g]) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(NULL); return; }
+        if (mvgcuda_clone_images(ctxs[g], ctxs[0]) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(ctxs[g]); return; }
+      }
+      mvgcuda_ctx* ctx = ctxs[g];
       const int64_t b = bounds[g], e = bounds[g + 1];
       mvgcuda_pair_matches pm;
-      if (mvgcuda_upload_images(ctx, n, desc.data(), rows.data(), 0) != MVGCUDA_OK ||
-          mvgcuda_set_features(ctx, n, xy.data(), rows.data()) != MVGCUDA_OK ||
-          mvgcuda_match_collection(ctx, e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
+      if (mvgcuda_match_collection(ctx, e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
         errors[g] = mvgcuda_last_error(ctx);
-        mvgcuda_destroy(ctx);
         return;
       }
       shard_out[g].resize(e - b);
@@ -105,11 +113,14 @@ class MatcherCudaAllInMemory : public Matcher {
         const int32_t* m = pm.matches + 2 * pm.offsets[p];
         for (int k = 0; k < pm.counts[p]; ++k) v.push_back(IndexedMatch(m[2 * k], m[2 * k + 1]));
       }
-      mvgcuda_destroy(ctx);
     };
-    std::vector<std::thread> th;
-    for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
-    for (auto& t : th) t.join();
+    if (errors[0].empty()) {
+      std::vector<std::thread> th;
+      for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
+      for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < gpus; ++g)
+      if (ctxs[g]) mvgcuda_destroy(ctxs[g]);  // only after every replica has been taken
     for (int g = 0; g < gpus; ++g) {
       if (!errors[g].empty()) {
         std::cerr << "MatcherCudaAllInMemory: GPU " << g << ": " << errors[g] << std::endl;

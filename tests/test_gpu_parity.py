@@ -219,6 +219,28 @@ def test_rescan_of_ambiguous_queries_real_sift(ctx, pkg, l1, et, rho, rescan_row
         ctx.set_tuning()
 
 
+def test_clone_images_replica(ctx, pkg, l1):
+    """mvgcuda_clone_images: a second context takes its arena (and features) from the first device to device -- the
+    path the multi-GPU driver uses instead of one PCIe upload per GPU -- and matches identically."""
+    descs = synth.collection(12, 4, 900) + [synth.uniform_set(3, 0)]          # incl. an empty image
+    feats = [synth.features(12, k, len(d)).reshape(-1, 4)[:, :2].copy() for k, d in enumerate(descs)]
+    ctx.upload_images(descs)
+    ctx.set_features(feats)
+    pairs = pkg.pairs_exhaustive(len(descs))
+    rs = float(pkg.square_f32(0.8))
+    want = ctx.match_collection(pairs, rs)
+    with pkg.Context(0) as replica:
+        replica.clone_images_from(ctx)
+        ctx.upload_images([synth.uniform_set(1, 300)])                          # the source may move on afterwards
+        got = replica.match_collection(pairs, rs)
+        assert np.array_equal(got.counts, want.counts) and np.array_equal(got.matches, want.matches)
+        for p in (0, 3, 5):
+            i, j = pairs[p]
+            assert np.array_equal(got.pair(p), l1.dedup_xy(l1.pair_matches(descs[i], descs[j], rs), feats[i], feats[j]))
+        with pytest.raises(pkg.MvgCudaError):
+            replica.clone_images_from(replica)
+
+
 # ---------------------------------------------------------------- collection level + export (rows 7-14)
 
 @pytest.mark.parametrize("r", [0.6, 0.8])
