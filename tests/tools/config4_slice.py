@@ -4,7 +4,7 @@ through the reference's own pairedIndexedMatchImport / PairedIndexedMatchToStrea
 present) -- the file-boundary acceptance check of SURVEY.md 8(d) config 4.  Log kept under profiles/."""
 import hashlib, importlib, os, sys, tempfile, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 pkg = importlib.import_module("3dreconstruction_b200")
 from oracle import oracle
 

@@ -1,8 +1,8 @@
 """BASELINE configs[3] / configs[4] at FULL size, strong-scaled over the GPUs of one box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 \
-        scripts/config_full.py --config 4          # 1,000 images x 8,000 SIFT  -> 499,500 pairs
-        scripts/config_full.py --config 5          #   200 images x 40,000 SIFT ->  19,900 pairs
+        tests/tools/config_full.py --config 4          # 1,000 images x 8,000 SIFT  -> 499,500 pairs
+        tests/tools/config_full.py --config 5          #   200 images x 40,000 SIFT ->  19,900 pairs
 
 Every rank generates 1/N of the seeded synthetic collection, the descriptor blocks are all-gathered over NVLink into a
 staging buffer and copied device-to-device into each GPU's replicated arena (no collective on the data
@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("3dreconstruction_b200")
 sharding = importlib.import_module("3dreconstruction_b200.sharding")

@@ -1,7 +1,7 @@
 """Quick GPU check used while tuning the kernel: exactness on a few shapes vs the L1 oracle + kernel throughput."""
 import importlib, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 pkg = importlib.import_module("3dreconstruction_b200")
 from oracle import oracle
 synth = pkg.synth

@@ -2,7 +2,7 @@
 level, all bit-exact against the L1 oracle.  Log kept under profiles/."""
 import importlib, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 pkg = importlib.import_module("3dreconstruction_b200")
 from oracle import oracle
 l1 = oracle.L1()
