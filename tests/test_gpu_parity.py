@@ -324,6 +324,12 @@ def test_full_size_40k_tiled_epilogue(ctx, pkg, l1):
     got = ctx.knn2_arrays(a, b, pkg.TIE_REFERENCE)
     _assert_knn_equal(got, want[0], want[1], "40k")
     assert got[0].max() > 65535 // 2
+    # pair level at the same size: the batch is long enough for the filter-first epilogue schedule, with pruning and the
+    # exact second pass on top
+    ctx.upload_images([a, b])
+    rs = float(pkg.square_f32(0.8))
+    res = ctx.match_pairs(np.array([[0, 1]], np.int32), rs)
+    assert np.array_equal(res.pair(0), l1.pair_matches(a, b, rs))
 
 
 def test_config3_slice_vs_oracle_and_properties(ctx, pkg, l1):
