@@ -202,7 +202,10 @@ __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const
     const int c1 = min(g1t, l1t);
     const int c2 = __vimin3_s32(max(g1t, l1t), l2 >> 8, g2t);
     const bool passes = __int2float_rn(qn + c1) < __fmul_rn(prune_ratio, __int2float_rn(qn + c2));
-    // failing: admit d <= rho * d(c1), rounded up (rho = 1 gives exactly c1)
+    // failing: admit d <= rho * d(c1), rounded up (rho = 1 gives exactly c1).  With rho < 1 a failing query may even miss
+    // its true nearest row (one within rho..1 of the recorded one cannot pass the test either); what stays exact is every
+    // pass/fail decision and the nearest row of every passing query -- after the second pass over the records that
+    // flag_ambiguous_kernel cannot decide (tests/test_pruning_model.py checks the rule).
     const int tf = __float2int_ru(__fmul_ru(prune_rho, __int2float_rn(qn + c1))) - qn;
     T = min(T, passes ? c2 : tf);
     ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
