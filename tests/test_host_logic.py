@@ -116,3 +116,19 @@ def test_shard_world2_gloo(tmp_path):
     assert sum(p[0] for p in r["parts"]) == r["total"] and sum(p[1] for p in r["parts"]) == r["sum"]
     assert r["parts"][0][3] == r["parts"][1][2] and r["parts"][0][2] == 0 and r["parts"][1][3] == r["total"]
     assert r["max"] == 2.0
+
+
+def test_rbtree_dedup_restatement_matches_std_set(tmp_path):
+    """experiments/rbtree_dedup.h (device-compatible restatement of libstdc++'s std::set range construction for the
+    reference's non-strict-weak coordinate comparator, SURVEY 8(a) row 13) against the real std::set, on the CPU."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = tmp_path / "test_rbtree"
+    src = os.path.join(ROOT, "tests", "native", "test_rbtree_dedup.cpp")
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-o", str(exe), src])
+    r = subprocess.run([str(exe), "8000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rbtree_dedup == std::set" in r.stdout
