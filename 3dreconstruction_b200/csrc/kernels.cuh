@@ -12,23 +12,15 @@
 #pragma once
 #include "ptx.cuh"
 
-#ifndef MVGCUDA_EXPERIMENT
-#define MVGCUDA_EXPERIMENT 0  // developer probes only (see epi_chunk16: 1 drain, 2/5/6/7 filter ladder, 3 counters); 0 = the product
-#endif
-#if MVGCUDA_EXPERIMENT == 3
-__device__ unsigned long long g_dbg[8];  // [0] chunks, [1] slow chunks, [2] group hits, [3] lane hits (chunk level)
-__device__ __forceinline__ unsigned int* dbg_smem() { __shared__ unsigned int a[8]; return a; }
-#define DBG_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&dbg_smem()[i], (unsigned int)(v)); } while (0)
-#else
-#define DBG_ADD(i, v) do { } while (0)
+#ifndef MVGCUDA_PROBE
+#define MVGCUDA_PROBE 0  // developer ceilings only (results wrong): 1 TMEM drain, 2 fast filter path, 8 TMA+MMA feed; 0 = the product
 #endif
 
 namespace mvgcuda {
 
 constexpr int kDim = 128;      // descriptor bytes == GEMM K
-constexpr int kBlockQ = 128;   // query rows per block   (MMA M, one TMEM lane per query)
-constexpr int kTileDb = 256;   // db rows per tile       (MMA N, one TMEM column per db row)
-constexpr int kStagesB = 4;    // db tile ring (TMA -> MMA)
+constexpr int kBlockQ = 128;   // query rows per block   (MMA M per CTA, one TMEM lane per query)
+constexpr int kTileDb = 256;   // db rows per tile       (one TMEM column per db row)
 constexpr int kSlotsA = 2;     // query block double buffer
 constexpr int kSlotsC = 8;     // per-column constant ring (TMA -> epilogue), outlives the B stage
 constexpr int kAccBufs = 2;    // TMEM accumulator double buffer (2 x 256 columns = all 512)
@@ -36,7 +28,8 @@ constexpr int kRowAlign = 256; // every image starts at a multiple of this in th
 constexpr int kPadNorm = 0x7FFFFF;  // "norm" of padding rows: > 128*255^2, so they never win
 
 constexpr uint32_t kBytesA = kBlockQ * kDim;        // 16 KB
-constexpr uint32_t kBytesB = kTileDb * kDim;        // 32 KB
+constexpr uint32_t kBytesB = kTileDb * kDim;        // 32 KB of db rows per tile (a CTA pair holds 16 KB each)
+constexpr uint32_t kBytesBRing = 4 * kBytesB;       // db tile ring (TMA -> MMA): 4 stages of 32 KB, or 8 of 16 KB per CTA of a pair
 constexpr int kChunk = 16;                     // db rows per filter decision in the epilogue
 constexpr int kTileC = kTileDb + kTileDb / kChunk;  // per-tile constants: 256 packed (norm<<8|col) + 16 chunk-min norms
 constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
@@ -46,6 +39,25 @@ constexpr int kNumEpiWarps = 4 * kEpiParts;
 constexpr int kPartCols = kTileDb / 2;                // 128 columns of every other tile per warp
 constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer
 constexpr int kKnnThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);  // 576 threads -> 112 registers per thread
+
+// Pipeline shapes (template parameters of knn2_kernel):
+//   kPair   two CTAs of a cluster (one TPC) work on two query blocks of the same pair with ONE tcgen05.mma.cta_group::2
+//           per K step (M = 256): each CTA stages only half of every db tile, so the shared-memory read rate of the tensor
+//           pipe per SM drops from 96 to 64 B/clk (N = 256) -- the single-CTA N = 128 shape needs 128 B/clk and starves
+//           (profiles/r02a_variants.log) -- and the L2 -> shared traffic per SM halves.
+//   kSplit  (pair only) a tile is issued as two N = 128 MMA groups with their own barriers: four accumulator buffers of
+//           128 columns instead of two of 256, so a buffer goes back to the MMA warp as soon as ITS four warps have
+//           drained it, and the TMEM drain of one buffer no longer sits on the critical path of the next MMA.
+template <bool kPair, bool kSplit>
+struct KnnShape {
+  static_assert(kPair || !kSplit, "N = 128 MMAs starve on shared-memory bandwidth without the CTA pair");
+  static constexpr int kStagesB = kPair ? 8 : 4;
+  static constexpr uint32_t kStageBytes = kBytesBRing / kStagesB;  // per CTA
+  static constexpr int kAccBars = kSplit ? 2 * kAccBufs : kAccBufs;
+  static constexpr int kMmaN = kSplit ? kPartCols : kTileDb;
+  static constexpr int kMmaM = kPair ? 2 * kBlockQ : kBlockQ;
+  static constexpr int kBoxDb = kPair ? (kSplit ? 64 : 128) : 256;  // rows of one TMA box of the db tensor map
+};
 
 struct PairJob {
   int db_row0;  // arena row of image I (db), multiple of kRowAlign
@@ -61,14 +73,16 @@ struct KnnRecord {  // one per query
   int d1, d2;       // exact squared distances
 };
 
+template <bool kPair, bool kSplit>
 struct KnnSmem {
+  using Shape = KnnShape<kPair, kSplit>;
   alignas(1024) uint8_t a[kSlotsA][kBytesA];
-  alignas(1024) uint8_t b[kStagesB][kBytesB];
-  alignas(16) int c[kSlotsC][kTileC];
+  alignas(1024) uint8_t b[Shape::kStagesB][Shape::kStageBytes];
+  alignas(16) int c[kSlotsC][2 * kTileC];  // schedules 0/1 use one tile per slot, schedule 2 a tile pair
   uint64_t a_full[kSlotsA], a_empty[kSlotsA];
-  uint64_t b_full[kStagesB], b_empty[kStagesB];
-  uint64_t c_full[kSlotsC], c_empty[kSlotsC];
-  uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
+  uint64_t b_full[Shape::kStagesB], b_empty[Shape::kStagesB];
+  uint64_t c_full[kSlotsC], c_empty[kSlotsC];  // (epilogue_slices relies on c_empty following c_full)
+  uint64_t acc_full[Shape::kAccBars], acc_empty[Shape::kAccBars];
   uint32_t tmem_base;
   int bound[2][kBlockQ];  // per (item parity, query): best-known 2nd-smallest t, atomically tightened by all parts
   alignas(16) int4 xchg[2][kEpiParts - 1][kBlockQ];  // parts 1.. hand their top-2 to part 0 at the end of an item
@@ -76,6 +90,7 @@ struct KnnSmem {
 
 struct KnnParams {
   const int* __restrict__ ccol;        // K1 output, [arena_rows / 256][kTileC]: per-row constants of the db operand
+  const int* __restrict__ hmin;        // tail of K1's output: min ||d||^2 of every 128 db rows
   const int* __restrict__ qcol;        // same layout for the rows the QUERY tensor map addresses (== ccol, except rescans)
   const PairJob* __restrict__ jobs;    // [n_jobs]
   const int* __restrict__ item_start;  // [n_jobs+1] prefix sum of query blocks per job
@@ -90,15 +105,21 @@ struct KnnParams {
 };
 
 // ------------------------------------------------------------------------------------------ K1
-// Per-row constants, laid out per 256-row tile as [256 x ((||d||^2 << 8) | col)] [16 x min ||d||^2 of each 16-row chunk].
-// 8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles; 32 rows (2 chunks) per block.
+// Per-row constants, laid out per 256-row tile as [256 x ((||d||^2 << 8) | col)] [16 x min ||d||^2 of each 16-row chunk],
+// followed (after the last tile) by one min ||d||^2 per 128 rows -- the filter constant of one epilogue warp's slice of a
+// tile, which the warp keeps in a register.  8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles;
+// 128 rows per block.
 __device__ __forceinline__ int ccol_index(int row) { return (row >> 8) * kTileC + (row & 255); }
+__host__ __device__ constexpr size_t ccol_ints(int arena_rows) {
+  return static_cast<size_t>(arena_rows / kTileDb) * kTileC + static_cast<size_t>(arena_rows / kPartCols);
+}
+constexpr int kK1Rows = kPartCols;  // rows per block of K1
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(8 * kK1Rows)
 row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img_row0, const int* __restrict__ img_rows,
                   int n_images, int arena_rows, int* __restrict__ ccol) {
-  __shared__ int norms[32];
-  const int row = blockIdx.x * 32 + (threadIdx.x >> 3);  // arena_rows is a multiple of 256
+  __shared__ int norms[kK1Rows];
+  const int row = blockIdx.x * kK1Rows + (threadIdx.x >> 3);  // arena_rows is a multiple of 256
   const int part = threadIdx.x & 7;
   const uint4 v = *reinterpret_cast<const uint4*>(arena + (size_t)row * kDim + part * 16);
   unsigned s = 0;
@@ -122,12 +143,17 @@ row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img
     ccol[ccol_index(row)] = (norm << 8) | (row & 255);
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
-    int m = norms[threadIdx.x * 16];
+  if (threadIdx.x < kK1Rows / kChunk) {
+    int m = norms[threadIdx.x * kChunk];
 #pragma unroll
-    for (int k = 1; k < 16; ++k) m = min(m, norms[threadIdx.x * 16 + k]);
-    const int row0 = blockIdx.x * 32 + threadIdx.x * 16;
+    for (int k = 1; k < kChunk; ++k) m = min(m, norms[threadIdx.x * kChunk + k]);
+    const int row0 = blockIdx.x * kK1Rows + threadIdx.x * kChunk;
     ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = m;
+    // minimum of the block's 128 rows (8 chunk minima live in the first 8 lanes of warp 0)
+    m = min(m, __shfl_xor_sync(0xffu, m, 1));
+    m = min(m, __shfl_xor_sync(0xffu, m, 2));
+    m = min(m, __shfl_xor_sync(0xffu, m, 4));
+    if (threadIdx.x == 0) ccol[static_cast<size_t>(arena_rows / kTileDb) * kTileC + blockIdx.x] = m;
   }
 }
 
@@ -140,12 +166,6 @@ __device__ __forceinline__ void locate_item(const KnnParams& p, int item, int& j
   }
   job = lo;
   qb = item - p.item_start[lo];
-}
-
-// Streaming exact top-2 of packed keys ((||d||^2 - 2 q.d) << 8 | column): 3 min/max per element.
-__device__ __forceinline__ void top2_insert(int& l1, int& l2, int p) {
-  l2 = min(l2, max(l1, p));
-  l1 = min(l1, p);
 }
 
 // Sorted pair (lo <= hi) helpers for the exact top-2 of a chunk: a merge tree has depth ~10 and plenty of
@@ -169,7 +189,6 @@ __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const
                                             const int cmin, const int g1t, const int g2t, const int qn,
                                             const float prune_ratio, const float prune_rho, const uint32_t bound_saddr,
                                             const int two, int& l1, int& l2, int& T) {
-    DBG_ADD(1, 1);
     // which groups of 4 rows can still matter (all four votes issued back to back)
     const bool h0 = __any_sync(0xffffffffu, two * g[0] + T >= cmin);
     const bool h1 = __any_sync(0xffffffffu, two * g[1] + T >= cmin);
@@ -179,7 +198,6 @@ __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (h[k]) {
-        DBG_ADD(2, 1);
         const int4 cc = ptx::lds128(cs_saddr + 16 * k);  // warp-uniform address: smem broadcast
         const int p0 = static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(x[4 * k + 0]));
         const int p1 = static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(x[4 * k + 1]));
@@ -222,37 +240,16 @@ __device__ __forceinline__ void epi_exact16(const int32_t* __restrict__ x, const
 __device__ __forceinline__ void epi_chunk16(const int32_t* __restrict__ x, const uint32_t cs_saddr, const int cmin,
                                             const int g1t, const int g2t, const int qn, const float prune_ratio, const float prune_rho,
                                             const uint32_t bound_saddr, const int two, int& l1, int& l2, int& T) {
-#if MVGCUDA_EXPERIMENT == 1  // TMEM drain only: no filter work at all (results wrong; pipeline ceiling probe)
+#if MVGCUDA_PROBE == 1  // TMEM drain only: no filter work at all
   l1 = min(l1, x[0]);
   return;
 #endif
   const int m = max16(x);  // 8 ops; the per-group maxima are only formed when the chunk goes to the exact step
-#if MVGCUDA_EXPERIMENT == 2  // fast path only (results wrong; filter cost probe)
+#if MVGCUDA_PROBE == 2  // fast path only
   l1 = min(l1, m + T + cmin);
   return;
 #endif
-#if MVGCUDA_EXPERIMENT == 5  // fast path + vote, no branch (results wrong)
-  l1 = min(l1, __any_sync(0xffffffffu, two * m + T >= cmin) ? m : l1);
-  return;
-#endif
-#if MVGCUDA_EXPERIMENT == 6  // fast path + vote + branch to a trivial exact step (results wrong)
   if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
-    l1 = min(l1, m);
-    T = min(T, l1);
-    ptx::red_min_shared(bound_saddr, T);
-  }
-  return;
-#endif
-  DBG_ADD(0, 1);
-#if MVGCUDA_EXPERIMENT == 3
-  const int dbg_lane_hits = __popc(__ballot_sync(0xffffffffu, two * m + T >= cmin));  // all lanes vote, lane 0 records
-  DBG_ADD(3, dbg_lane_hits);
-#endif
-#if MVGCUDA_EXPERIMENT == 7  // the real exact step compiled in but never taken (static cost probe; results wrong)
-  if (__any_sync(0xffffffffu, two * m + T >= cmin) && two == 3) {
-#else
-  if (__any_sync(0xffffffffu, two * m + T >= cmin)) {
-#endif
     int g[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) g[k] = max(__vimax3_s32(x[4 * k], x[4 * k + 1], x[4 * k + 2]), x[4 * k + 3]);
@@ -265,27 +262,209 @@ constexpr int kTInit = 0x3FFFFFFF;  // "no bound yet": 2*x + kTInit cannot overf
 // (t, index) lexicographic order: smaller distance first, lower db row on ties
 __device__ __forceinline__ bool cand_less(int ta, int ia, int tb, int ib) { return ta < tb || (ta == tb && ia < ib); }
 
-// kDeferred selects the epilogue schedule of a tile (both are bit-identical in their results):
-//   false  in place: each chunk is filtered and, if needed, examined exactly while it sits in registers; the TMEM loads
-//          rotate through four register sets.  Best up to ~10-20k db rows.
-//   true   filter first: all eight chunks are reduced to their maxima, the few that still matter are loaded a second
-//          time for the exact step (one rolled copy).  First tiles of an item cost more (every chunk matters and is
-//          loaded twice), later tiles less: +10 % at 40k rows, -10 % at 2k rows, equal at 10k (profiles/r01l_*).
-template <bool kDeferred>
-__global__ void __launch_bounds__(kKnnThreads, 1)
+// End of a tile in which some chunk was examined exactly (schedule 2): merge the tile's top-2 (packed keys l1 <= l2) into
+// the running top-2 -- ties keep the earlier (lower) index; branch-free selects; an untouched l1/l2 (0x7FFFFFFF) decodes
+// to t = 0x7FFFFF, larger than any real t -- and tighten the bound (ratio-aware pruning, see epi_exact16).
+__device__ __forceinline__ void slice_commit(const int l1, const int l2, const int t, const int qn, const float prune_ratio,
+                                             const float prune_rho, const uint32_t bound_saddr, int& g1t, int& g1i, int& g2t,
+                                             int& g2i, int& T) {
+  const int base = t * kTileDb;
+  const int t1 = l1 >> 8, i1 = base + (l1 & 255);
+  const int t2 = l2 >> 8, i2 = base + (l2 & 255);
+  const bool a = t1 < g1t, b = t2 < g1t, c = t1 < g2t;
+  const int n2t = a ? (b ? t2 : g1t) : (c ? t1 : g2t);
+  const int n2i = a ? (b ? i2 : g1i) : (c ? i1 : g2i);
+  g1t = a ? t1 : g1t;
+  g1i = a ? i1 : g1i;
+  g2t = n2t;
+  g2i = n2i;
+  // g1t <= g2t are now the two smallest t of rows this warp has really seen
+  const bool passes = __int2float_rn(qn + g1t) < __fmul_rn(prune_ratio, __int2float_rn(qn + g2t));
+  const int tf = __float2int_ru(__fmul_ru(prune_rho, __int2float_rn(qn + g1t))) - qn;
+  T = min(T, passes ? g2t : tf);
+  ptx::red_min_shared(bound_saddr, T);  // the warps scanning the other columns of these queries tighten their filter now
+}
+
+// ===================== epilogue, schedule 2 ("slices") =====================
+// Warp (quad, g, sub) owns TMEM lanes 32*quad.., and of EVERY tile the 64 columns [128 g + 64 sub, +64): four 16-column
+// chunks = 64 registers, loaded at once.  The accumulator buffer is handed back to the MMA warp as soon as those loads
+// have landed -- before any arithmetic -- so the time a buffer spends outside the tensor pipe is one TMEM-load latency
+// instead of a filter pass (in the other schedules that hand-back sits on the critical path of the next MMA into the
+// buffer; profiles/r02e: MMA warp 32 % of its time in acc_empty waits, epilogue warps 18 % in acc_full waits).
+// The epilogue is bound by instruction issue (4 warps per scheduler), so the hot path is kept to the minimum:
+//   * filter: a row of the slice can only matter if ||d||^2 - 2 q.d <= T, hence only if 2 q.d >= hm - T with
+//     hm = min ||d||^2 of the tile half (one prefetched register): 35 max ops over the 64 raw dot products, ONE compare,
+//     one vote, one branch per tile -- no shared memory, no per-chunk control flow;
+//   * tiles are walked two at a time, so every barrier / TMEM address of a step is a loop-invariant register and the
+//     barrier phases are two bits that flip (an item always starts in accumulator buffer 0);
+//   * only when some lane passes: which chunks (four votes), exact packed keys of ALL 16 rows of those chunks straight
+//     from the registers, top-2 merge, ONE bound update and ONE merge into the running top-2 per tile.
+// The first tile of an item skips the filter (no useful bound yet).
+__device__ __forceinline__ void top2_of4(const int32_t* __restrict__ x, const int4 cc, int& l1, int& l2) {
+  const int p0 = static_cast<int>(static_cast<uint32_t>(cc.x) - 512u * static_cast<uint32_t>(x[0]));
+  const int p1 = static_cast<int>(static_cast<uint32_t>(cc.y) - 512u * static_cast<uint32_t>(x[1]));
+  const int p2 = static_cast<int>(static_cast<uint32_t>(cc.z) - 512u * static_cast<uint32_t>(x[2]));
+  const int p3 = static_cast<int>(static_cast<uint32_t>(cc.w) - 512u * static_cast<uint32_t>(x[3]));
+  const Pair2 c = merge2(sort2(p0, p1), sort2(p2, p3));
+  const int nl2 = __vimin3_s32(max(l1, c.lo), l2, c.hi);
+  l1 = min(l1, c.lo);
+  l2 = nl2;
+}
+// exact packed keys ((||d||^2 - 2 q.d) << 8 | column) of all 16 rows of a chunk, merged into the tile's top-2
+__device__ __forceinline__ void exact_chunk_all(const int32_t* __restrict__ x, const uint32_t cs_saddr, int& l1, int& l2) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) top2_of4(x + 4 * k, ptx::lds128(cs_saddr + 16 * k), l1, l2);
+}
+
+// Values the compiler must keep in a register instead of re-deriving them (it otherwise rematerialises the aligned base
+// of the dynamic shared memory -- a dozen uniform-datapath instructions -- in front of every barrier access of the loop).
+__device__ __forceinline__ uint32_t keep_reg(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+
+template <bool kPair, bool kSplit>
+__device__ __forceinline__ void epilogue_slices(KnnSmem<kPair, kSplit>& s, const KnnParams& p, const uint32_t tmem_base,
+                                                const int warp, const int lane, const uint32_t rank, const int worker,
+                                                const int n_workers) {
+  using Smem = KnnSmem<kPair, kSplit>;
+  const int quad = warp & 3;  // a warp may only touch its own TMEM lane quadrant
+  const int part = (warp - kFirstEpiWarp) >> 2;
+  const int g = part >> 1;    // column half of the tile == its own accumulator buffer when kSplit
+  const int sub = part & 1;   // 64-column slice of that half
+  const int row = quad * 32 + lane;
+  const uint32_t tslice = keep_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + g * kPartCols + sub * 64);
+  // loop-invariant shared-memory addresses (32-bit, shared space): the two accumulator buffers' barriers of half g,
+  // the constants ring, this query's bound slots
+  const uint32_t sbase = ptx::smem_u32(&s);
+  const uint32_t full0 = keep_reg(sbase + offsetof(Smem, acc_full) + 8u * (kSplit ? g : 0));
+  const uint32_t full1 = keep_reg(sbase + offsetof(Smem, acc_full) + 8u * (kSplit ? 2 + g : 1));
+  uint32_t e0 = sbase + offsetof(Smem, acc_empty) + 8u * (kSplit ? g : 0);
+  uint32_t e1 = sbase + offsetof(Smem, acc_empty) + 8u * (kSplit ? 2 + g : 1);
+  if constexpr (kPair) { e0 = ptx::mapa_shared(e0, 0); e1 = ptx::mapa_shared(e1, 0); }
+  const uint32_t empty0 = keep_reg(e0), empty1 = keep_reg(e1);
+  const uint32_t c_ring = keep_reg(sbase + offsetof(Smem, c) + static_cast<uint32_t>(g * kPartCols + sub * 64) * 4u);  // the slice's per-column constants in slot 0
+  const uint32_t c_bars = keep_reg(sbase + offsetof(Smem, c_full));
+  const uint32_t bound0 = keep_reg(sbase + offsetof(Smem, bound) + 4u * row);
+  uint32_t ph = 0;     // bit b: parity of the next acc_full phase of buffer b
+  uint32_t c_cnt = 0;  // tile PAIRS seen so far == position in the constants ring (one slot holds two tiles)
+  uint32_t item_it = 0;
+  ptx::sts32(bound0, kTInit);
+  ptx::sts32(bound0 + 4u * kBlockQ, kTInit);
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");
+  for (int item = worker; item < p.n_items; item += n_workers, ++item_it) {
+    int job, qb;
+    locate_item(p, item, job, qb);
+    if constexpr (kPair) qb = 2 * qb + static_cast<int>(rank);
+    const PairJob J = p.jobs[job];
+    const int q_local = qb * kBlockQ + row;
+    const bool q_ok = q_local < J.q_rows;
+    const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
+    const int qn = p.qcol[ccol_index(J.q_row0 + min(q_local, J.q_rows - 1))] >> 8;  // ||q||^2 (dist = qn + t)
+    int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;  // running best two (t-domain) of this thread's columns
+    int T = kTInit;                                              // admit t <= T
+    const uint32_t bound_saddr = bound0 + (item_it & 1u) * (4u * kBlockQ);
+    ptx::sts32(bound0 + ((item_it & 1u) ^ 1u) * (4u * kBlockQ), kTInit);  // idle slot (every part left the previous item at the barrier below)
+    const int* hm_ptr = p.hmin + (J.db_row0 >> 7) + g;  // min ||d||^2 of tile t's half g: hm_ptr[2 t]
+    int hm_next = ntiles > 0 ? __ldg(hm_ptr) : 0;
+
+    // One tile in accumulator buffer kBuf (compile-time): everything indexed by the buffer is a loop invariant.
+#define MVG_TILE_STEP(kBuf, t_expr)                                                                                       \
+    {                                                                                                                      \
+      const int t = (t_expr);                                                                                              \
+      ptx::mbar_wait_addr(kBuf ? full1 : full0, (ph >> kBuf) & 1u);                                                        \
+      ph ^= (1u << kBuf);                                                                                                  \
+      ptx::tc_fence_after();                                                                                               \
+      int32_t v0[16], v1[16], v2[16], v3[16];                                                                              \
+      ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb, v0);                                                                \
+      ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 16, v1);                                                           \
+      ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 32, v2);                                                           \
+      ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 48, v3);                                                           \
+      const int hm = hm_next;                                                                                              \
+      hm_ptr += 2;                                                                                                         \
+      if (t + 1 < ntiles) hm_next = __ldg(hm_ptr);                                                                         \
+      T = min(T, ptx::lds32_volatile(bound_saddr));                                                                        \
+      ptx::tmem_ld_wait_for4(v0, v1, v2, v3);                                                                              \
+      ptx::tc_fence_before();                                                                                              \
+      __syncwarp();                                                                                                        \
+      if (lane == 0) { /* the buffer goes back to the MMA warp now */                                                      \
+        if constexpr (kPair) ptx::mbar_arrive_cluster(kBuf ? empty1 : empty0);                                             \
+        else ptx::mbar_arrive_addr(kBuf ? empty1 : empty0);                                                                \
+      }                                                                                                                    \
+      const int m0 = max16(v0), m1 = max16(v1), m2 = max16(v2), m3 = max16(v3);                                            \
+      const int thr = (hm - T + 1) >> 1; /* 2 m >= hm - T  <=>  m >= ceil((hm - T) / 2) */                                 \
+      if (__any_sync(0xffffffffu, max(__vimax3_s32(m0, m1, m2), m3) >= thr) || t == 0) {                                   \
+        const uint32_t sc = c_cnt & (kSlotsC - 1);                                                                         \
+        ptx::mbar_wait_addr(c_bars + 8u * sc, (c_cnt / kSlotsC) & 1); /* per-column constants: on this path only */        \
+        const uint32_t cs = c_ring + sc * (2u * kBytesC) + kBuf * kBytesC;                                                 \
+        int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;                                                                              \
+        const bool first = t == 0;                                                                                         \
+        if (first || __any_sync(0xffffffffu, m0 >= thr)) exact_chunk_all(v0, cs, l1, l2);                                  \
+        if (first || __any_sync(0xffffffffu, m1 >= thr)) exact_chunk_all(v1, cs + 64, l1, l2);                             \
+        if (first || __any_sync(0xffffffffu, m2 >= thr)) exact_chunk_all(v2, cs + 128, l1, l2);                            \
+        if (first || __any_sync(0xffffffffu, m3 >= thr)) exact_chunk_all(v3, cs + 192, l1, l2);                            \
+        slice_commit(l1, l2, t, qn, p.prune_ratio, p.prune_rho, bound_saddr, g1t, g1i, g2t, g2i, T);                       \
+      }                                                                                                                    \
+    }
+    for (int tp = 0; tp < ntiles; tp += 2) {
+      MVG_TILE_STEP(0, tp)
+      if (tp + 1 < ntiles) MVG_TILE_STEP(1, tp + 1)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_addr(c_bars + 8u * (kSlotsC + (c_cnt & (kSlotsC - 1))));  // c_empty follows c_full in KnnSmem
+      ++c_cnt;
+    }
+#undef MVG_TILE_STEP
+    // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record
+    if (part > 0) s.xchg[item_it & 1][part - 1][row] = make_int4(g1t, g1i, g2t, g2i);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");  // the warps sharing these 32 queries
+    if (part == 0 && q_ok) {
+      int b1t = g1t, b1i = g1i, b2t = g2t, b2i = g2i;
+#pragma unroll
+      for (int o_ = 0; o_ < kEpiParts - 1; ++o_) {
+        const int4 o = s.xchg[item_it & 1][o_][row];
+        if (cand_less(o.x, o.y, b1t, b1i)) {
+          if (cand_less(o.z, o.w, b1t, b1i)) { b2t = o.z; b2i = o.w; } else { b2t = b1t; b2i = b1i; }
+          b1t = o.x; b1i = o.y;
+        } else if (cand_less(o.x, o.y, b2t, b2i)) {
+          b2t = o.x; b2i = o.y;
+        }
+      }
+      KnnRecord r;
+      r.idx1 = b1i; r.idx2 = b2i; r.d1 = qn + b1t; r.d2 = qn + b2t;
+      *reinterpret_cast<int4*>(&p.out[J.out_off + q_local]) = *reinterpret_cast<const int4*>(&r);
+    }
+  }
+}
+
+// kSched selects the epilogue schedule of a tile (all are bit-identical in their results):
+//   0  in place: each chunk is filtered and, if needed, examined exactly while it sits in registers; the TMEM loads
+//      rotate through four register sets.
+//   1  filter first: all eight chunks are reduced to their maxima, the few that still matter are loaded a second
+//      time for the exact step (one rolled copy).  First tiles of an item cost more (every chunk matters and is
+//      loaded twice), later tiles less.
+//   2  slices: every warp takes 64 columns of EVERY tile and hands the accumulator back before any arithmetic
+//      (epilogue_slices above).
+// kPair / kSplit: see KnnShape.  In a pair the work item is (image pair, TWO consecutive query blocks): the CTA of cluster
+// rank r owns block 2*item + r (an odd last block leaves rank 1 with no valid query; it still takes part in the MMAs).
+template <int kSched, bool kPair, bool kSplit>
+__global__ void __launch_bounds__(kKnnThreads, 1)  // 18 warps: two schedulers host 5 warps, so 16 K / 5 warps = 96 registers per thread
 knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 B
-            const __grid_constant__ CUtensorMap tmap_db,  // box 256 rows x 128 B
+            const __grid_constant__ CUtensorMap tmap_db,  // box KnnShape::kBoxDb rows x 128 B
             const KnnParams p) {
+  using Shape = KnnShape<kPair, kSplit>;
+  using Smem = KnnSmem<kPair, kSplit>;
+  constexpr int kStagesB = Shape::kStagesB;
+  constexpr int kAccBars = Shape::kAccBars;
   extern __shared__ uint8_t smem_raw[];
-  KnnSmem& s = *reinterpret_cast<KnnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // warp / lane through a shuffle: values ptxas cannot rematerialise.  Derived directly from %tid they are re-read with
   // S2R (~25 clocks, and a dependent shift) inside the tile loop instead of being kept in a register.
   const int lane = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x & 31), static_cast<int>(threadIdx.x & 31));
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;        // 0 = leader: issues the MMAs of the pair
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-#if MVGCUDA_EXPERIMENT == 3
-  if (threadIdx.x < 8) dbg_smem()[threadIdx.x] = 0;
-#endif
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_db);
@@ -293,49 +472,109 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(&s.a_full[i], 1); ptx::mbar_init(&s.a_empty[i], 1); }
     for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(&s.b_full[i], 1); ptx::mbar_init(&s.b_empty[i], 1); }
-    // a tile is consumed by the 8 epilogue warps of one tile-parity group
-    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kNumEpiWarps / 2); }
-    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&s.acc_full[i], 1); ptx::mbar_init(&s.acc_empty[i], kNumEpiWarps / 2); }
+    // a tile's constants are consumed by the 8 epilogue warps of one tile-parity group (of this CTA)
+    for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kSched == 2 ? kNumEpiWarps : kNumEpiWarps / 2); }
+    // an accumulator buffer goes back to the (leader's) MMA warp when its warps of BOTH CTAs of a pair have drained it
+    for (int i = 0; i < kAccBars; ++i) {
+      ptx::mbar_init(&s.acc_full[i], 1);
+      ptx::mbar_init(&s.acc_empty[i], (kPair ? 2 : 1) * (kSched == 2 ? 2 : 1) * kNumEpiWarps / kAccBars);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc<512>(&s.tmem_base);
+  if (warp == 0) {
+    if constexpr (kPair) ptx::tmem_alloc_pair<512>(&s.tmem_base); else ptx::tmem_alloc<512>(&s.tmem_base);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    {
       uint32_t a_it = 0, b_it = 0, c_it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a_it) {
+      for (int item = worker; item < p.n_items; item += n_workers, ++a_it) {
         int job, qb;
         locate_item(p, item, job, qb);
+        if constexpr (kPair) qb = 2 * qb + static_cast<int>(rank);
         const PairJob J = p.jobs[job];
         const uint32_t sa = a_it % kSlotsA;
         ptx::mbar_wait(&s.a_empty[sa], ((a_it / kSlotsA) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&s.a_full[sa], kBytesA);
-        ptx::tma_load_2d(s.a[sa], &tmap_q, 0, J.q_row0 + qb * kBlockQ, &s.a_full[sa]);
+        if (ptx::elect_one()) {
+          if constexpr (kPair) {
+            // both CTAs load their own query block; the bytes of both are counted on the leader's barrier
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&s.a_full[sa], 2 * kBytesA);
+            ptx::tma_load_2d_pair(s.a[sa], &tmap_q, 0, J.q_row0 + qb * kBlockQ, ptx::mapa_shared(ptx::smem_u32(&s.a_full[sa]), 0));
+          } else {
+            ptx::mbar_arrive_expect_tx(&s.a_full[sa], kBytesA);
+            ptx::tma_load_2d(s.a[sa], &tmap_q, 0, J.q_row0 + qb * kBlockQ, &s.a_full[sa]);
+          }
+        }
+        __syncwarp();
         const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
-        for (int t = 0; t < ntiles; ++t, ++b_it, ++c_it) {
-          const uint32_t sc = c_it % kSlotsC;
-          ptx::mbar_wait(&s.c_empty[sc], ((c_it / kSlotsC) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&s.c_full[sc], kBytesC);
-          ptx::bulk_load_1d(s.c[sc], p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, kBytesC, &s.c_full[sc]);
+        for (int t = 0; t < ntiles; ++t, ++b_it) {
+#if MVGCUDA_PROBE != 8
+          if constexpr (kSched == 2) {
+            if ((t & 1) == 0) {  // one ring slot per tile PAIR (the constants of consecutive tiles are contiguous)
+              const uint32_t sc = c_it % kSlotsC;
+              ptx::mbar_wait(&s.c_empty[sc], ((c_it / kSlotsC) & 1) ^ 1);
+              if (ptx::elect_one()) {
+                const uint32_t bytes = (t + 1 < ntiles ? 2u : 1u) * kBytesC;
+                ptx::mbar_arrive_expect_tx(&s.c_full[sc], bytes);
+                ptx::bulk_load_1d(s.c[sc], p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, bytes, &s.c_full[sc]);
+              }
+              __syncwarp();
+              ++c_it;
+            }
+          } else {
+            const uint32_t sc = c_it % kSlotsC;
+            ptx::mbar_wait(&s.c_empty[sc], ((c_it / kSlotsC) & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&s.c_full[sc], kBytesC);
+              ptx::bulk_load_1d(s.c[sc], p.ccol + (size_t)((J.db_row0 >> 8) + t) * kTileC, kBytesC, &s.c_full[sc]);
+            }
+            __syncwarp();
+            ++c_it;
+          }
+#endif
           const uint32_t sb = b_it % kStagesB;
           ptx::mbar_wait(&s.b_empty[sb], ((b_it / kStagesB) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&s.b_full[sb], kBytesB);
-          ptx::tma_load_2d(s.b[sb], &tmap_db, 0, J.db_row0 + t * kTileDb, &s.b_full[sb]);
+          const int row0 = J.db_row0 + t * kTileDb;
+          if (ptx::elect_one()) {
+            if constexpr (kPair) {
+              // this CTA stages HALF of the tile: the rows its SM feeds to the pair's MMAs (B is split along N).
+              // N = 256: rank r supplies columns [128 r, 128 r + 128).  N = 128 (kSplit): MMA group h covers tile rows
+              // [128 h, 128 h + 128) and rank r supplies its columns [64 r, 64 r + 64): two boxes of 64 rows.
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&s.b_full[sb], kBytesB);
+              const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(&s.b_full[sb]), 0);
+              if constexpr (kSplit) {
+                ptx::tma_load_2d_pair(s.b[sb], &tmap_db, 0, row0 + 64 * static_cast<int>(rank), bar);
+                ptx::tma_load_2d_pair(s.b[sb] + 64 * kDim, &tmap_db, 0, row0 + kPartCols + 64 * static_cast<int>(rank), bar);
+              } else {
+                ptx::tma_load_2d_pair(s.b[sb], &tmap_db, 0, row0 + kPartCols * static_cast<int>(rank), bar);
+              }
+            } else {
+              ptx::mbar_arrive_expect_tx(&s.b_full[sb], kBytesB);
+              ptx::tma_load_2d(s.b[sb], &tmap_db, 0, row0, &s.b_full[sb]);
+            }
+          }
+          __syncwarp();
         }
       }
+      if constexpr (kPair) {
+        // Do not leave (and let the CTA's shared memory go) while commits of the leader can still arrive here: the last
+        // a_empty commit of the pair follows every other commit, wait for it.
+        if (a_it > 0) ptx::mbar_wait(&s.a_empty[(a_it - 1) % kSlotsA], ((a_it - 1) / kSlotsA) & 1);
+      }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(kBlockQ, kTileDb);
+    // ===================== MMA issuer (in a pair: of the leader CTA) =====================
+    // The whole warp walks the loop (uniform control flow, uniform addresses); one elected lane issues.
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(Shape::kMmaM, Shape::kMmaN);
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a_it) {
+      uint32_t eph = 0;  // schedule 2: bit `bar` = uses of that accumulator barrier so far, mod 2
+      for (int item = worker; item < p.n_items; item += n_workers, ++a_it) {
         int job, qb;
         locate_item(p, item, job, qb);
         const int db_rows = p.jobs[job].db_rows;
@@ -345,22 +584,50 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         const int ntiles = (db_rows + kTileDb - 1) / kTileDb;
         for (int t = 0; t < ntiles; ++t, ++b_it, ++acc_it) {
           const uint32_t sb = b_it % kStagesB;
-          const uint32_t buf = acc_it % kAccBufs;
+          // schedule 2 starts every item in buffer 0 (its epilogue walks tiles in pairs with fixed buffers)
+          const uint32_t buf = kSched == 2 ? static_cast<uint32_t>(t & 1) : acc_it % kAccBufs;
           ptx::mbar_wait(&s.b_full[sb], (b_it / kStagesB) & 1);
-          ptx::mbar_wait(&s.acc_empty[buf], ((acc_it / kAccBufs) & 1) ^ 1);
-          ptx::tc_fence_after();
           const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(s.b[sb]));
           const uint32_t tmem_d = tmem_base + buf * kTileDb;
+          constexpr int kGroups = kSplit ? 2 : 1;
 #pragma unroll
-          for (int k = 0; k < kDim / 32; ++k)  // K = 32 bytes per kind::i8 instruction
-            ptx::mma_i8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          ptx::mma_commit(&s.b_empty[sb]);    // db stage reusable once these MMAs have read it
-          ptx::mma_commit(&s.acc_full[buf]);  // accumulator ready for the epilogue
+          for (int h = 0; h < kGroups; ++h) {
+            const uint32_t bar = kSplit ? 2 * buf + h : buf;
+#if MVGCUDA_PROBE != 8
+            if constexpr (kSched == 2) {
+              ptx::mbar_wait(&s.acc_empty[bar], ((eph >> bar) & 1u) ^ 1u);
+              eph ^= 1u << bar;
+            } else {
+              ptx::mbar_wait(&s.acc_empty[bar], ((acc_it / kAccBufs) & 1) ^ 1);
+            }
+#endif
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kDim / 32; ++k) {  // K = 32 bytes per kind::i8 instruction
+                if constexpr (kPair)  // group h reads this CTA's rows [64 h, 64 h + 64) of the stage (8 KB further)
+                  ptx::mma_i8_ss_pair(tmem_d + h * kPartCols, adesc + 2 * k, bdesc + h * (64 * kDim / 16) + 2 * k, idesc, k > 0);
+                else
+                  ptx::mma_i8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+              }
+              if constexpr (kPair) {
+                if (h == kGroups - 1) ptx::mma_commit_pair(&s.b_empty[sb]);  // db stage of BOTH CTAs reusable
+                ptx::mma_commit_pair(&s.acc_full[bar]);                      // accumulator ready in both CTAs
+              } else {
+                ptx::mma_commit(&s.b_empty[sb]);    // db stage reusable once these MMAs have read it
+                ptx::mma_commit(&s.acc_full[bar]);  // accumulator ready for the epilogue
+              }
+              if (t == ntiles - 1 && h == kGroups - 1) {  // query slot reusable
+                if constexpr (kPair) ptx::mma_commit_pair(&s.a_empty[sa]); else ptx::mma_commit(&s.a_empty[sa]);
+              }
+            }
+            __syncwarp();
+          }
         }
-        ptx::mma_commit(&s.a_empty[sa]);  // query slot reusable
       }
     }
-    __syncwarp();
+  } else if constexpr (kSched == 2 && MVGCUDA_PROBE == 0) {
+    epilogue_slices<kPair, kSplit>(s, p, tmem_base, warp, lane, rank, worker, n_workers);
   } else {
     // ===================== epilogue: kEpiParts threads per query row =====================
     // Warp (quad, half, par) owns TMEM lanes 32*quad.., columns [128*half, 128*half+128) of the tiles whose running
@@ -374,16 +641,24 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     const int two = p.two;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + par * kTileDb + half * kPartCols;
     uint32_t acc_it = 0, c_it = 0, item_it = 0;
+    const uint32_t acc_bar = kSplit ? 2 * par + static_cast<uint32_t>(half) : par;
+    // where "this buffer is drained" is reported: the barrier of the CTA that issues the MMAs
+    const uint32_t acc_empty_addr = kPair ? ptx::mapa_shared(ptx::smem_u32(&s.acc_empty[acc_bar]), 0) : ptx::smem_u32(&s.acc_empty[acc_bar]);
     s.bound[0][row] = kTInit;
     s.bound[1][row] = kTInit;
     asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_it) {
+    for (int item = worker; item < p.n_items; item += n_workers, ++item_it) {
       int job, qb;
       locate_item(p, item, job, qb);
+      if constexpr (kPair) qb = 2 * qb + static_cast<int>(rank);
       const PairJob J = p.jobs[job];
       const int q_local = qb * kBlockQ + row;
       const bool q_ok = q_local < J.q_rows;
+#if MVGCUDA_PROBE == 8  // TMA + MMA feed ceiling: the epilogue never touches a tile
+      const int ntiles = 0;
+#else
       const int ntiles = (J.db_rows + kTileDb - 1) / kTileDb;
+#endif
       const int qn = p.qcol[ccol_index(J.q_row0 + min(q_local, J.q_rows - 1))] >> 8;  // ||q||^2 (dist = qn + t)
       // running best two of this thread's columns in the t-domain, t = ||d||^2 - 2 q.d  (dist = ||q||^2 + t)
       int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;
@@ -395,16 +670,16 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         const uint32_t acc = acc_it + t, cc_it = c_it + t;
         const uint32_t sc = cc_it % kSlotsC;
         ptx::mbar_wait(&s.c_full[sc], (cc_it / kSlotsC) & 1);
-        ptx::mbar_wait(&s.acc_full[par], (acc >> 1) & 1);
+        ptx::mbar_wait(&s.acc_full[acc_bar], (acc >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t cs = ptx::smem_u32(s.c[sc] + half * kPartCols);
         int l1 = 0x7FFFFFFF, l2 = 0x7FFFFFFF;
         int T = min(min(g2t, kTInit), ptx::lds32_volatile(bound_saddr));  // admit t <= T
         const uint32_t cm_saddr = ptx::smem_u32(s.c[sc] + kTileDb + half * (kPartCols / kChunk));
+        if constexpr (kSched == 1 && MVGCUDA_PROBE == 0) {
         const int4 cm0 = ptx::lds128(cm_saddr);
         const int4 cm1 = ptx::lds128(cm_saddr + 16);
-        if constexpr (kDeferred && MVGCUDA_EXPERIMENT == 0) {
-        // Filter first, exact step later (the variant launched for long scans, see launch_knn_raw).  The filter needs only the maximum of a chunk, so the 16 registers of a chunk
+        // Filter first, exact step later.  The filter needs only the maximum of a chunk, so the 16 registers of a chunk
         // are dead eight max ops after they arrive and the whole 128-column slice drains in two batches of four loads.
         // Per lane one bit per chunk records "some row of this chunk may still matter" (bound as of the tile start:
         // conservative, the bound only shrinks); the OR over the warp (one REDUX) says which chunks need the exact
@@ -452,8 +727,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
+        if (lane == 0) { if constexpr (kPair) ptx::mbar_arrive_cluster(acc_empty_addr); else ptx::mbar_arrive(&s.acc_empty[acc_bar]); }
         } else {
+        const int4 cm0 = ptx::lds128(cm_saddr);
+        const int4 cm1 = ptx::lds128(cm_saddr + 16);
         // Eight chunks of 16 columns through four register sets.  tcgen05.wait::ld waits for EVERY outstanding load, so
         // each load is issued one chunk ahead of the wait that covers it: only the first wait of a tile sees the TMEM
         // latency.  The accumulator goes back to the MMA warp as soon as the last chunk is in registers.
@@ -484,7 +761,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::tmem_ld_wait_for(v3);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&s.acc_empty[par]);
+        if (lane == 0) { if constexpr (kPair) ptx::mbar_arrive_cluster(acc_empty_addr); else ptx::mbar_arrive(&s.acc_empty[acc_bar]); }
         MVG_CHUNK(v1, 5, cm1.y);
         T = min(T, ptx::lds32_volatile(bound_saddr));
         MVG_CHUNK(v2, 6, cm1.z);
@@ -509,8 +786,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
           g2i = n2i;
         }
       }
+#if MVGCUDA_PROBE == 8
+      acc_it += (J.db_rows + kTileDb - 1) / kTileDb;
+#else
       acc_it += ntiles;
       c_it += ntiles;
+#endif
       // parts 1.. hand their result to part 0, which merges by (t, row) and writes the record
       if (part > 0) s.xchg[item_it & 1][part - 1][row] = make_int4(g1t, g1i, g2t, g2i);
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");  // the warps sharing these 32 queries
@@ -534,11 +815,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
-#if MVGCUDA_EXPERIMENT == 3
-  if (threadIdx.x < 8) atomicAdd(&g_dbg[threadIdx.x], (unsigned long long)dbg_smem()[threadIdx.x]);
-#endif
+  if constexpr (kPair) ptx::cluster_sync_all(); else __syncthreads();  // pair: no CTA leaves while its peer may still signal it
+  if (warp == 0) {
+    if constexpr (kPair) ptx::tmem_dealloc_pair<512>(tmem_base); else ptx::tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ probe

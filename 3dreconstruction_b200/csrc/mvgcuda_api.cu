@@ -95,7 +95,8 @@ struct Arena {
   DevBuf<int> img_row0, img_rows;
   std::vector<int> row0, rows;  // host copies
   int arena_rows = 0;
-  CUtensorMap tmap_q, tmap_db;
+  CUtensorMap tmap_q, tmap_db;   // boxes of 128 rows (query block; half a db tile for a CTA pair) and 256 rows (db tile)
+  CUtensorMap tmap_db64;         // boxes of 64 rows (a CTA pair's share of one N = 128 MMA group)
   void release() { desc.release(); ccol.release(); img_row0.release(); img_rows.release(); row0.clear(); rows.clear(); arena_rows = 0; }
 };
 
@@ -142,6 +143,7 @@ struct mvgcuda_ctx {
   int tmap_resc_rows = 0;
   long long rescanned = 0;  // queries matched a second time by the last match call
   int force_epilogue = -1;  // -1 auto (by db size), 0 in place, 1 filter first; env MVGCUDA_EPILOGUE, for tests
+  int pipe = 0;             // 0 one CTA per work item, 1 CTA pair (cta_group::2, N = 256), 2 CTA pair with N = 128 groups; env MVGCUDA_PIPE
   PinnedBuf<long long> h_total;
 
   // results of the last match call
@@ -221,7 +223,7 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   A.row0[n_images] = (int)total;
   A.arena_rows = (int)std::max<long long>(total, kRowAlign);
   CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
-  CU_CHECK(ctx, A.ccol.reserve((size_t)(A.arena_rows / kTileDb) * kTileC));
+  CU_CHECK(ctx, A.ccol.reserve(ccol_ints(A.arena_rows)));
   CU_CHECK(ctx, A.img_row0.reserve(n_images + 1));
   CU_CHECK(ctx, A.img_rows.reserve(std::max(n_images, 1)));
   cudaStream_t st = ctx->stream;
@@ -237,12 +239,14 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   if (n_images)
     CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
-  row_consts_kernel<<<A.arena_rows / 32, 256, 0, st>>>(A.desc.p, A.img_row0.p, A.img_rows.p, n_images, A.arena_rows,
+  row_consts_kernel<<<A.arena_rows / kK1Rows, 8 * kK1Rows, 0, st>>>(A.desc.p, A.img_row0.p, A.img_rows.p, n_images, A.arena_rows,
                                                        A.ccol.p);
   CU_CHECK(ctx, cudaGetLastError());
   int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
   if (rc) return rc;
   rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &A.tmap_db64, A.desc.p, A.arena_rows, 64);
   if (rc) return rc;
   CU_CHECK(ctx, cudaStreamSynchronize(st));  // row0/rows vectors and caller buffers are free again
   return MVGCUDA_OK;
@@ -271,7 +275,8 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
     j.valid = (j.db_rows >= 2 && j.q_rows >= 1) ? 1 : 0;
     ctx->h_item_start.p[p - p0] = items;
     if (j.valid) {
-      const int ni = (j.q_rows + kBlockQ - 1) / kBlockQ;
+      const int nblocks = (j.q_rows + kBlockQ - 1) / kBlockQ;
+      const int ni = ctx->pipe ? (nblocks + 1) / 2 : nblocks;  // a CTA pair takes two query blocks per item
       items += ni;
       db_sum += (long long)ni * j.db_rows;
     }
@@ -285,15 +290,49 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
 
 // `deferred`: the filter-first epilogue schedule, which pays off for long scans (see knn2_kernel).
 constexpr int kDeferredMinDbRows = 20000;
-static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp,
-                          bool deferred) {
+
+template <int kSched, bool kPair, bool kSplit>
+static cudaError_t launch_knn_shape(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp) {
+  const int sms = ctx->prop.multiProcessorCount;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kKnnThreads);
+  cfg.dynamicSmemBytes = ctx->knn_smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  if (kPair) {
+    cfg.gridDim = dim3(2 * std::min(kp.n_items, sms / 2));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(kp.n_items, sms));
+  }
+  return cudaLaunchKernelEx(&cfg, knn2_kernel<kSched, kPair, kSplit>, tmap_q, tmap_db, kp);
+}
+
+template <int kSched>
+static cudaError_t launch_knn_sched(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const Arena& A, const KnnParams& kp) {
+  switch (ctx->pipe) {
+    case 0: return launch_knn_shape<kSched, false, false>(ctx, tmap_q, A.tmap_db, kp);
+    case 1: return launch_knn_shape<kSched, true, false>(ctx, tmap_q, A.tmap_q, kp);
+    default: return launch_knn_shape<kSched, true, true>(ctx, tmap_q, A.tmap_db64, kp);
+  }
+}
+
+// tmap_q: boxes of 128 query rows; A: the arena the db rows live in (its tensor map with the box of the pipeline shape)
+// sched: epilogue schedule 0 in place, 1 filter first, 2 lean (see knn2_kernel)
+static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const Arena& A, const KnnParams& kp, int sched) {
   if (kp.n_items == 0) return MVGCUDA_OK;
-  const int grid = std::min(kp.n_items, ctx->prop.multiProcessorCount);
-  if (deferred)
-    knn2_kernel<true><<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
-  else
-    knn2_kernel<false><<<grid, kKnnThreads, ctx->knn_smem, ctx->stream>>>(tmap_q, tmap_db, kp);
-  CU_CHECK(ctx, cudaGetLastError());
+  cudaError_t e;
+  switch (sched) {
+    case 0: e = launch_knn_sched<0>(ctx, tmap_q, A, kp); break;
+    case 1: e = launch_knn_sched<1>(ctx, tmap_q, A, kp); break;
+    default: e = launch_knn_sched<2>(ctx, tmap_q, A, kp); break;
+  }
+  CU_CHECK(ctx, e);
   return MVGCUDA_OK;
 }
 
@@ -301,6 +340,7 @@ static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUt
 static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, float prune_ratio, float prune_rho) {
   KnnParams kp;
   kp.ccol = A.ccol.p;
+  kp.hmin = A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC;
   kp.qcol = A.ccol.p;
   kp.jobs = ctx->d_jobs.p;
   kp.item_start = ctx->d_item_start.p;
@@ -310,8 +350,8 @@ static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, flo
   kp.two = 2;
   kp.prune_ratio = prune_ratio;
   kp.prune_rho = prune_rho;
-  const bool deferred = ctx->force_epilogue >= 0 ? ctx->force_epilogue != 0 : bp.mean_db_rows >= kDeferredMinDbRows;
-  return launch_knn_raw(ctx, A.tmap_q, A.tmap_db, kp, deferred);
+  const int sched = ctx->force_epilogue >= 0 ? ctx->force_epilogue : (bp.mean_db_rows >= kDeferredMinDbRows ? 1 : 0);
+  return launch_knn_raw(ctx, A.tmap_q, A, kp, sched);
 }
 
 constexpr long long kBatchRecords = 24ll << 20;  // queries per batch (384 MB of KnnRecord)
@@ -369,7 +409,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
   ctx->rescanned += total;
   const int cap = (int)std::min<long long>(std::max(ctx->rescan_cap_rows, 1), round_up((int)std::min<long long>(total, 1 << 30), 256));
   const size_t ccol_len = (size_t)(cap / kTileDb + 2) * kTileC;
-  CU_CHECK(ctx, ctx->d_resc_desc.reserve((size_t)(cap + kBlockQ) * kDim));
+  CU_CHECK(ctx, ctx->d_resc_desc.reserve((size_t)(cap + 2 * kBlockQ) * kDim));
   CU_CHECK(ctx, ctx->d_resc_ccol.reserve(ccol_len));
   CU_CHECK(ctx, ctx->d_resc_knn.reserve(cap));
   const int tm_rows = (int)(ctx->d_resc_desc.cap / kDim);
@@ -413,7 +453,8 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     }
     for (int k = 0; k < n_rj; ++k) {
       ctx->h_ritem_start.p[k] = items;
-      items += (ctx->h_rjobs.p[k].q_rows + kBlockQ - 1) / kBlockQ;
+      const int nblocks = (ctx->h_rjobs.p[k].q_rows + kBlockQ - 1) / kBlockQ;
+      items += ctx->pipe ? (nblocks + 1) / 2 : nblocks;
     }
     if (n_rj == 0) break;
     ctx->h_ritem_start.p[n_rj] = items;
@@ -426,6 +467,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     CU_CHECK(ctx, cudaGetLastError());
     KnnParams kp;
     kp.ccol = A.ccol.p;
+    kp.hmin = A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC;
     kp.qcol = ctx->d_resc_ccol.p;
     kp.jobs = ctx->d_rjobs.p;
     kp.item_start = ctx->d_ritem_start.p;
@@ -435,7 +477,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     kp.two = 2;
     kp.prune_ratio = FLT_MAX;
     kp.prune_rho = 1.0f;
-    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A.tmap_db, kp, ctx->force_epilogue > 0);
+    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A, kp, std::max(ctx->force_epilogue, 0));
     if (rc) return rc;
     rescan_scatter_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
     CU_CHECK(ctx, cudaGetLastError());
@@ -735,17 +777,30 @@ int mvgcuda_create(int device, mvgcuda_ctx** out) {
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
-  ctx->knn_smem = sizeof(KnnSmem) + 1024;
-  if ((e = cudaFuncSetAttribute(knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
-    return fail("cudaFuncSetAttribute(knn2_kernel<false>)", e);
-  if ((e = cudaFuncSetAttribute(knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
-    return fail("cudaFuncSetAttribute(knn2_kernel<true>)", e);
+  ctx->knn_smem = sizeof(KnnSmem<false, false>) + 1024;
+  static_assert(sizeof(KnnSmem<true, false>) == sizeof(KnnSmem<false, false>) && sizeof(KnnSmem<true, true>) <= sizeof(KnnSmem<false, false>) + 64,
+                "the pipeline shapes share one shared-memory budget");
+  ctx->knn_smem = std::max(ctx->knn_smem, sizeof(KnnSmem<true, true>) + 1024);
+  {
+    const void* fns[9] = {(const void*)knn2_kernel<0, false, false>, (const void*)knn2_kernel<1, false, false>, (const void*)knn2_kernel<2, false, false>,
+                          (const void*)knn2_kernel<0, true, false>,  (const void*)knn2_kernel<1, true, false>,  (const void*)knn2_kernel<2, true, false>,
+                          (const void*)knn2_kernel<0, true, true>,   (const void*)knn2_kernel<1, true, true>,   (const void*)knn2_kernel<2, true, true>};
+    for (const void* fn : fns)
+      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(knn2_kernel)", e);
+  }
   if ((e = cudaFuncSetAttribute(i8_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kBytesA + kBytesB + 1024))) != cudaSuccess)
     return fail("cudaFuncSetAttribute(probe)", e);
   if (const char* ep = getenv("MVGCUDA_EPILOGUE")) {  // test knob: force one epilogue schedule (results never differ)
     if (!strcmp(ep, "deferred")) ctx->force_epilogue = 1;
     else if (!strcmp(ep, "inplace")) ctx->force_epilogue = 0;
+    else if (!strcmp(ep, "lean")) ctx->force_epilogue = 2;
+  }
+  if (const char* pp = getenv("MVGCUDA_PIPE")) {  // test knob: force one pipeline shape (results never differ)
+    if (!strcmp(pp, "single")) ctx->pipe = 0;
+    else if (!strcmp(pp, "pair")) ctx->pipe = 1;
+    else if (!strcmp(pp, "pairsplit")) ctx->pipe = 2;
   }
   *out = ctx;
   return MVGCUDA_OK;
@@ -844,7 +899,7 @@ int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src) {
   A.rows = S.rows;
   A.arena_rows = S.arena_rows;
   const int n_images = (int)A.rows.size();
-  const size_t ccol_len = (size_t)(A.arena_rows / kTileDb) * kTileC;
+  const size_t ccol_len = ccol_ints(A.arena_rows);
   CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
   CU_CHECK(ctx, A.ccol.reserve(ccol_len));
   CU_CHECK(ctx, A.img_row0.reserve(n_images + 1));
@@ -858,6 +913,8 @@ int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src) {
   int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
   if (rc) return rc;
   rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &A.tmap_db64, A.desc.p, A.arena_rows, 64);
   if (rc) return rc;
   CU_CHECK(ctx, cudaStreamSynchronize(st));
   return MVGCUDA_OK;
@@ -1032,7 +1089,7 @@ int mvgcuda_probe_i8_peak(mvgcuda_ctx* ctx, int iters, double* ops_per_sec, floa
   return MVGCUDA_OK;
 }
 
-#if MVGCUDA_EXPERIMENT == 3
+#if 0
 // developer probe builds only (not part of include/mvgcuda.h)
 int mvgcuda_debug_counters(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
