@@ -95,8 +95,8 @@ struct Arena {
   DevBuf<int> img_row0, img_rows;
   std::vector<int> row0, rows;  // host copies
   int arena_rows = 0;
-  CUtensorMap tmap_q, tmap_db;   // boxes of 128 rows (query block; half a db tile for a CTA pair) and 256 rows (db tile)
-  CUtensorMap tmap_db64;         // boxes of 64 rows (a CTA pair's share of one N = 128 MMA group)
+  CUtensorMap tmap_q;    // boxes of 128 rows: one CTA's query block
+  CUtensorMap tmap_db;   // boxes of 64 rows: one CTA's share of an N = 128 MMA group
   void release() { desc.release(); ccol.release(); img_row0.release(); img_rows.release(); row0.clear(); rows.clear(); arena_rows = 0; }
 };
 
@@ -118,6 +118,7 @@ struct mvgcuda_ctx {
   // batch buffers
   DevBuf<PairJob> d_jobs;
   DevBuf<int> d_item_start;
+  DevBuf<KnnItem> d_items, d_ritems;  // work lists of K2 (batch / second pass)
   DevBuf<KnnRecord> d_knn;
   DevBuf<int2> d_tmp;
   DevBuf<int> d_npass, d_counts;
@@ -142,8 +143,6 @@ struct mvgcuda_ctx {
   const uint8_t* tmap_resc_base = nullptr;
   int tmap_resc_rows = 0;
   long long rescanned = 0;  // queries matched a second time by the last match call
-  int force_epilogue = -1;  // -1 auto (by db size), 0 in place, 1 filter first; env MVGCUDA_EPILOGUE, for tests
-  int pipe = 0;             // 0 one CTA per work item, 1 CTA pair (cta_group::2, N = 256), 2 CTA pair with N = 128 groups; env MVGCUDA_PIPE
   PinnedBuf<long long> h_total;
 
   // results of the last match call
@@ -244,9 +243,7 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
   CU_CHECK(ctx, cudaGetLastError());
   int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
   if (rc) return rc;
-  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
-  if (rc) return rc;
-  rc = make_tmap(ctx, &A.tmap_db64, A.desc.p, A.arena_rows, 64);
+  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, 64);
   if (rc) return rc;
   CU_CHECK(ctx, cudaStreamSynchronize(st));  // row0/rows vectors and caller buffers are free again
   return MVGCUDA_OK;
@@ -275,8 +272,7 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
     j.valid = (j.db_rows >= 2 && j.q_rows >= 1) ? 1 : 0;
     ctx->h_item_start.p[p - p0] = items;
     if (j.valid) {
-      const int nblocks = (j.q_rows + kBlockQ - 1) / kBlockQ;
-      const int ni = ctx->pipe ? (nblocks + 1) / 2 : nblocks;  // a CTA pair takes two query blocks per item
+      const int ni = (j.q_rows + 2 * kBlockQ - 1) / (2 * kBlockQ);  // a CTA pair takes two query blocks per item
       items += ni;
       db_sum += (long long)ni * j.db_rows;
     }
@@ -288,70 +284,41 @@ static void plan_batch(mvgcuda_ctx* ctx, const Arena& A, const int32_t* pairs, i
   bp.n_records = rec;
 }
 
-// `deferred`: the filter-first epilogue schedule, which pays off for long scans (see knn2_kernel).
-constexpr int kDeferredMinDbRows = 20000;
-
-template <int kSched, bool kPair, bool kSplit>
-static cudaError_t launch_knn_shape(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const KnnParams& kp) {
-  const int sms = ctx->prop.multiProcessorCount;
+// Work list + one persistent launch of K2.  tmap_q: boxes of 128 query rows; A: the arena the db rows live in.
+static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const Arena& A, KnnParams kp, const PairJob* d_jobs,
+                          const int* d_item_start, int n_jobs, DevBuf<KnnItem>& d_items) {
+  if (kp.n_items == 0) return MVGCUDA_OK;
+  CU_CHECK(ctx, d_items.reserve(kp.n_items));
+  build_items_kernel<<<(kp.n_items + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, d_item_start, n_jobs, kp.n_items, d_items.p);
+  CU_CHECK(ctx, cudaGetLastError());
+  kp.items = d_items.p;
+  kp.ccol = A.ccol.p;
+  kp.hmin = A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kKnnThreads);
+  cfg.gridDim = dim3(2 * std::min(kp.n_items, ctx->prop.multiProcessorCount / 2));  // CTA pairs
   cfg.dynamicSmemBytes = ctx->knn_smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
-  if (kPair) {
-    cfg.gridDim = dim3(2 * std::min(kp.n_items, sms / 2));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3(std::min(kp.n_items, sms));
-  }
-  return cudaLaunchKernelEx(&cfg, knn2_kernel<kSched, kPair, kSplit>, tmap_q, tmap_db, kp);
-}
-
-template <int kSched>
-static cudaError_t launch_knn_sched(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const Arena& A, const KnnParams& kp) {
-  switch (ctx->pipe) {
-    case 0: return launch_knn_shape<kSched, false, false>(ctx, tmap_q, A.tmap_db, kp);
-    case 1: return launch_knn_shape<kSched, true, false>(ctx, tmap_q, A.tmap_q, kp);
-    default: return launch_knn_shape<kSched, true, true>(ctx, tmap_q, A.tmap_db64, kp);
-  }
-}
-
-// tmap_q: boxes of 128 query rows; A: the arena the db rows live in (its tensor map with the box of the pipeline shape)
-// sched: epilogue schedule 0 in place, 1 filter first, 2 lean (see knn2_kernel)
-static int launch_knn_raw(mvgcuda_ctx* ctx, const CUtensorMap& tmap_q, const Arena& A, const KnnParams& kp, int sched) {
-  if (kp.n_items == 0) return MVGCUDA_OK;
-  cudaError_t e;
-  switch (sched) {
-    case 0: e = launch_knn_sched<0>(ctx, tmap_q, A, kp); break;
-    case 1: e = launch_knn_sched<1>(ctx, tmap_q, A, kp); break;
-    default: e = launch_knn_sched<2>(ctx, tmap_q, A, kp); break;
-  }
-  CU_CHECK(ctx, e);
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, knn2_kernel, tmap_q, A.tmap_db, kp));
   return MVGCUDA_OK;
 }
 
 // prune_ratio: the Lowe ratio the records will be tested against, or FLT_MAX for the exact 2-NN of every query.
 static int launch_knn(mvgcuda_ctx* ctx, const Arena& A, const BatchPlan& bp, float prune_ratio, float prune_rho) {
-  KnnParams kp;
-  kp.ccol = A.ccol.p;
-  kp.hmin = A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC;
+  KnnParams kp = {};
   kp.qcol = A.ccol.p;
-  kp.jobs = ctx->d_jobs.p;
-  kp.item_start = ctx->d_item_start.p;
-  kp.n_jobs = bp.n_jobs;
   kp.n_items = bp.n_items;
   kp.out = ctx->d_knn.p;
-  kp.two = 2;
   kp.prune_ratio = prune_ratio;
   kp.prune_rho = prune_rho;
-  const int sched = ctx->force_epilogue >= 0 ? ctx->force_epilogue : (bp.mean_db_rows >= kDeferredMinDbRows ? 1 : 0);
-  return launch_knn_raw(ctx, A.tmap_q, A, kp, sched);
+  return launch_knn_raw(ctx, A.tmap_q, A, kp, ctx->d_jobs.p, ctx->d_item_start.p, bp.n_jobs, ctx->d_items);
 }
 
 constexpr long long kBatchRecords = 24ll << 20;  // queries per batch (384 MB of KnnRecord)
@@ -453,8 +420,7 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     }
     for (int k = 0; k < n_rj; ++k) {
       ctx->h_ritem_start.p[k] = items;
-      const int nblocks = (ctx->h_rjobs.p[k].q_rows + kBlockQ - 1) / kBlockQ;
-      items += ctx->pipe ? (nblocks + 1) / 2 : nblocks;
+      items += (ctx->h_rjobs.p[k].q_rows + 2 * kBlockQ - 1) / (2 * kBlockQ);
     }
     if (n_rj == 0) break;
     ctx->h_ritem_start.p[n_rj] = items;
@@ -465,19 +431,13 @@ static int rescan_ambiguous(mvgcuda_ctx* ctx, const Arena& A, int nb, long long 
     rescan_gather_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, A.desc.p, A.ccol.p, ctx->d_resc_desc.p,
                                                ctx->d_resc_ccol.p);
     CU_CHECK(ctx, cudaGetLastError());
-    KnnParams kp;
-    kp.ccol = A.ccol.p;
-    kp.hmin = A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC;
+    KnnParams kp = {};
     kp.qcol = ctx->d_resc_ccol.p;
-    kp.jobs = ctx->d_rjobs.p;
-    kp.item_start = ctx->d_ritem_start.p;
-    kp.n_jobs = n_rj;
     kp.n_items = items;
     kp.out = ctx->d_resc_knn.p;
-    kp.two = 2;
     kp.prune_ratio = FLT_MAX;
     kp.prune_rho = 1.0f;
-    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A, kp, std::max(ctx->force_epilogue, 0));
+    int rc = launch_knn_raw(ctx, ctx->tmap_resc, A, kp, ctx->d_rjobs.p, ctx->d_ritem_start.p, n_rj, ctx->d_ritems);
     if (rc) return rc;
     rescan_scatter_kernel<<<n_rs, 256, 0, st>>>(ctx->d_rsrc.p, ctx->d_resc_idx.p, ctx->d_resc_knn.p, ctx->d_knn.p);
     CU_CHECK(ctx, cudaGetLastError());
@@ -777,31 +737,12 @@ int mvgcuda_create(int device, mvgcuda_ctx** out) {
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
-  ctx->knn_smem = sizeof(KnnSmem<false, false>) + 1024;
-  static_assert(sizeof(KnnSmem<true, false>) == sizeof(KnnSmem<false, false>) && sizeof(KnnSmem<true, true>) <= sizeof(KnnSmem<false, false>) + 64,
-                "the pipeline shapes share one shared-memory budget");
-  ctx->knn_smem = std::max(ctx->knn_smem, sizeof(KnnSmem<true, true>) + 1024);
-  {
-    const void* fns[9] = {(const void*)knn2_kernel<0, false, false>, (const void*)knn2_kernel<1, false, false>, (const void*)knn2_kernel<2, false, false>,
-                          (const void*)knn2_kernel<0, true, false>,  (const void*)knn2_kernel<1, true, false>,  (const void*)knn2_kernel<2, true, false>,
-                          (const void*)knn2_kernel<0, true, true>,   (const void*)knn2_kernel<1, true, true>,   (const void*)knn2_kernel<2, true, true>};
-    for (const void* fn : fns)
-      if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(knn2_kernel)", e);
-  }
+  ctx->knn_smem = sizeof(KnnSmem) + 1024;
+  if ((e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(knn2_kernel)", e);
   if ((e = cudaFuncSetAttribute(i8_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kBytesA + kBytesB + 1024))) != cudaSuccess)
     return fail("cudaFuncSetAttribute(probe)", e);
-  if (const char* ep = getenv("MVGCUDA_EPILOGUE")) {  // test knob: force one epilogue schedule (results never differ)
-    if (!strcmp(ep, "deferred")) ctx->force_epilogue = 1;
-    else if (!strcmp(ep, "inplace")) ctx->force_epilogue = 0;
-    else if (!strcmp(ep, "lean")) ctx->force_epilogue = 2;
-  }
-  if (const char* pp = getenv("MVGCUDA_PIPE")) {  // test knob: force one pipeline shape (results never differ)
-    if (!strcmp(pp, "single")) ctx->pipe = 0;
-    else if (!strcmp(pp, "pair")) ctx->pipe = 1;
-    else if (!strcmp(pp, "pairsplit")) ctx->pipe = 2;
-  }
   *out = ctx;
   return MVGCUDA_OK;
 }
@@ -812,7 +753,7 @@ void mvgcuda_destroy(mvgcuda_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->images.release();
   ctx->scratch.release();
-  ctx->d_jobs.release(); ctx->d_item_start.release(); ctx->d_knn.release(); ctx->d_tmp.release();
+  ctx->d_jobs.release(); ctx->d_item_start.release(); ctx->d_items.release(); ctx->d_ritems.release(); ctx->d_knn.release(); ctx->d_tmp.release();
   ctx->d_npass.release(); ctx->d_counts.release(); ctx->d_offsets.release(); ctx->d_total.release();
   ctx->d_matches.release();
   ctx->h_jobs.release(); ctx->h_item_start.release(); ctx->h_total.release();
@@ -912,9 +853,7 @@ int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src) {
     CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
   int rc = make_tmap(ctx, &A.tmap_q, A.desc.p, A.arena_rows, kBlockQ);
   if (rc) return rc;
-  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, kTileDb);
-  if (rc) return rc;
-  rc = make_tmap(ctx, &A.tmap_db64, A.desc.p, A.arena_rows, 64);
+  rc = make_tmap(ctx, &A.tmap_db, A.desc.p, A.arena_rows, 64);
   if (rc) return rc;
   CU_CHECK(ctx, cudaStreamSynchronize(st));
   return MVGCUDA_OK;

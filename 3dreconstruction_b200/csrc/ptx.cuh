@@ -63,11 +63,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU
-// box.  The wall clock is consulted every 64 failed polls; 2 s is far beyond any legitimate wait here.
+// box.  The wall clock is consulted every 64 failed polls; 2 s is far beyond any legitimate wait here.  (Build with
+// -DMVGCUDA_DEBUG_WAIT to have the trapping thread print which barrier it was waiting on; the printf costs registers in
+// every waiting loop, so the product only traps.)
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t saddr, uint32_t parity) {
+#ifdef MVGCUDA_DEBUG_WAIT
+  printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, saddr, parity);
+#endif
+  (void)saddr; (void)parity;
+  __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -77,15 +86,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++polls & 63u) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 2000000000ull) {
-        printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x,
-               smem_u32(bar), parity);
-        __trap();
-      }
+      if (now - t0 > 2000000000ull) mbar_timeout(smem_u32(bar), parity);
     }
   }
 }
-
 // same on raw shared-memory addresses (loop-invariant registers of the caller)
 __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t saddr, uint32_t parity) {
   uint32_t ok;
@@ -108,10 +112,7 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t saddr, uint32_t parity) 
     if ((++polls & 63u) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 2000000000ull) {
-        printf("mvgcuda: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, saddr, parity);
-        __trap();
-      }
+      if (now - t0 > 2000000000ull) mbar_timeout(saddr, parity);
     }
   }
 }
@@ -278,6 +279,50 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// ---------------------------------------------------------------- raw-address forms (32-bit shared-space addresses)
+// The hot loops of knn2_kernel keep shared-memory addresses in registers (see keep_reg in kernels.cuh).
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar_saddr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_addr(uint32_t dst_saddr, const CUtensorMap* tmap, int c0, int c1,
+                                                      uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_addr(uint32_t dst_saddr, const void* gmem_src, uint32_t bytes, uint32_t bar_saddr) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(bar_saddr)
+      : "memory");
+}
+// Low word of make_kmajor_sw128_desc (start address >> 4 | LBO << 16); the high word is the constant kDescHi.
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B >> 4, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t kmajor_sw128_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void mma_i8_pair_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_addr(uint32_t bar_saddr) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_saddr),
       "h"(static_cast<uint16_t>(3))
       : "memory");
 }
