@@ -37,8 +37,9 @@ constexpr uint32_t kBytesC = kTileC * sizeof(int);  // 1088 B
 
 constexpr int kEpiParts = 4;     // warps per TMEM lane quadrant; they share 32 queries, 64 columns of every tile each
 constexpr int kNumEpiWarps = 4 * kEpiParts;
-constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer
-constexpr int kKnnThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);  // 576 threads; two schedulers host 5 warps -> 96 registers per thread
+constexpr int kFirstEpiWarp = 2;                       // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer of group 0
+constexpr int kMmaWarp1 = kFirstEpiWarp + kNumEpiWarps;  // warp 18: MMA issuer of group 1
+constexpr int kKnnThreads = 32 * (kMmaWarp1 + 1);      // 608 threads; three schedulers host 5 warps -> 96 registers per thread
 
 struct PairJob {
   int db_row0;  // arena row of image I (db), multiple of kRowAlign
@@ -258,7 +259,7 @@ __device__ __forceinline__ uint32_t keep_reg(uint32_t x) {
 //   warp 0     TMA producer (both CTAs): query block (2 slots) per item, per tile two boxes of 64 db rows (8-stage ring)
 //              and, per tile pair, the per-column constants (2 x 1088 B bulk copy, 8-slot ring).  All loads of a pair
 //              signal the LEADER's barriers.
-//   warp 1     MMA issuer (leader CTA only).  Commits are multicast to the barriers of both CTAs.
+//   warps 1,18 MMA issuers (leader CTA only), one per MMA group of a tile.  Commits are multicast to the barriers of both CTAs.
 //   warps 2-17 epilogue, 4 per TMEM lane quadrant (= per scheduler).  Warp (quad, g, sub) owns lanes 32 quad.. and, of EVERY
 //              tile, the 64 columns [128 g + 64 sub, +64) = 64 registers, loaded at once; the accumulator buffer goes
 //              back to the MMA warp as soon as those loads have landed -- before any arithmetic -- so a buffer is away
@@ -291,8 +292,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     ptx::prefetch_tensormap(&tmap_db);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(&s.a_full[i], 1); ptx::mbar_init(&s.a_empty[i], 1); }
-    for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(&s.b_full[i], 1); ptx::mbar_init(&s.b_empty[i], 1); }
+    // a query slot / db stage is free again when BOTH MMA issuers' instructions have read it (one commit each)
+    for (int i = 0; i < kSlotsA; ++i) { ptx::mbar_init(&s.a_full[i], 1); ptx::mbar_init(&s.a_empty[i], 2); }
+    for (int i = 0; i < kStagesB; ++i) { ptx::mbar_init(&s.b_full[i], 1); ptx::mbar_init(&s.b_empty[i], 2); }
     // a tile pair's constants are used by all 16 epilogue warps of this CTA
     for (int i = 0; i < kSlotsC; ++i) { ptx::mbar_init(&s.c_full[i], 1); ptx::mbar_init(&s.c_empty[i], kNumEpiWarps); }
     // an accumulator buffer goes back to the leader's MMA warp when the 8 warps of its column half in BOTH CTAs have read it
@@ -356,16 +358,22 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     // Do not leave (and let the CTA's shared memory go) while commits of the leader can still arrive here: the last
     // a_empty commit of the pair follows every other commit, wait for it.
     if (a_it > 0) ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, a_empty) + 8u * ((a_it - 1) & 1u), ((a_it - 1) >> 1) & 1u);
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) =====================
-    if (rank == 0) {
+  } else if (warp == 1 || warp == kMmaWarp1) {
+    // ===================== MMA issuers (leader CTA): ONE elected lane of each runs the whole loop =====================
+    // Two warps on two schedulers: warp 1 issues MMA group 0 of every tile (tile rows [0, 128) -> accumulator buffers 0, 2),
+    // warp 18 group 1 (rows [128, 256) -> buffers 1, 3).  One issuer was the limit of the pipeline: ~100 instructions per tile,
+    // each a dependent step of a single thread that shares its scheduler with four epilogue warps (profiles/r02j).
+    // (elect.sync rather than `lane == 0`: the compiler then knows a single thread is active and feeds the uniform-datapath
+    // operands of UTCIMMA / UTCBAR with one R2UR each instead of a loop over lanes.)
+    if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_u8u8s32(2 * kBlockQ, kHalfCols);
+      const uint32_t h = warp == 1 ? 0u : 1u;
       const uint32_t sb_ = keep_reg(sbase);
       const uint32_t a_lo0 = keep_reg(ptx::kmajor_sw128_desc_lo(sb_ + offsetof(KnnSmem, a)));
-      const uint32_t b_lo0 = keep_reg(ptx::kmajor_sw128_desc_lo(sb_ + offsetof(KnnSmem, b)));
+      const uint32_t b_lo0 = keep_reg(ptx::kmajor_sw128_desc_lo(sb_ + offsetof(KnnSmem, b)) + h * (64 * kDim / 16));  // group h reads this CTA's rows [64 h, +64) of a stage
       uint32_t a_it = 0;
       uint32_t sb = 0, b_par = 0;  // B ring position; parity to wait for on b_full
-      uint32_t eph = 0xFu;         // bit `buf`: parity to wait for on acc_empty[buf] (fresh barriers pass parity 1)
+      uint32_t eph = 0x3u;         // bit (t & 1): parity to wait for on acc_empty of buffer 2 (t & 1) + h (fresh barriers pass parity 1)
       for (int item = worker; item < p.n_items; item += n_workers, ++a_it) {
         const int db_rows = p.items[item].db_rows;
         const uint32_t sa = a_it & 1u;
@@ -373,28 +381,24 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         const uint32_t a_lo = a_lo0 + sa * (kBytesA >> 4);
         const int ntiles = (db_rows + kTileDb - 1) / kTileDb;
         for (int t = 0; t < ntiles; ++t) {
+          const uint32_t tb = static_cast<uint32_t>(t & 1);  // every item starts in buffers 0 / 1
+          const uint32_t buf = 2u * tb + h;
           ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, b_full) + 8u * sb, b_par);
+          ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, acc_empty) + 8u * buf, (eph >> tb) & 1u);
+          eph ^= 1u << tb;
+          ptx::tc_fence_after();
           const uint32_t b_lo = b_lo0 + sb * (kStageBytes >> 4);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t buf = (static_cast<uint32_t>(t & 1) << 1) | h;  // every item starts in buffer 0
-            ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, acc_empty) + 8u * buf, (eph >> buf) & 1u);
-            eph ^= 1u << buf;
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kDim / 32; ++k)  // K = 32 bytes per kind::i8 instruction; group h reads this CTA's rows [64 h, +64) of the stage
-                ptx::mma_i8_pair_lo(tmem_base + buf * kHalfCols, a_lo + 2 * k, b_lo + h * (64 * kDim / 16) + 2 * k, idesc, k > 0);
-              if (h == 1) ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, b_empty) + 8u * sb);  // db stage of BOTH CTAs reusable
-              ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, acc_full) + 8u * buf);            // accumulator ready in both CTAs
-              if (h == 1 && t == ntiles - 1) ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, a_empty) + 8u * sa);  // query slots reusable
-            }
-            __syncwarp();
-          }
+          for (int k = 0; k < kDim / 32; ++k)  // K = 32 bytes per kind::i8 instruction
+            ptx::mma_i8_pair_lo(tmem_base + buf * kHalfCols, a_lo + 2 * k, b_lo + 2 * k, idesc, k > 0);
+          ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, acc_full) + 8u * buf);  // accumulator ready in both CTAs
+          ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, b_empty) + 8u * sb);    // this issuer is done with the db stage (both CTAs)
+          if (t == ntiles - 1) ptx::mma_commit_pair_addr(sb_ + offsetof(KnnSmem, a_empty) + 8u * sa);  // ... and with the query slots
           if (++sb == kStagesB) { sb = 0; b_par ^= 1u; }
         }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int quad = warp & 3;  // a warp may only touch its own TMEM lane quadrant
