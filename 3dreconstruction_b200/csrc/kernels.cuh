@@ -13,6 +13,7 @@
 #include <cstddef>
 
 #include "ptx.cuh"
+#include "rbtree_dedup.cuh"
 
 namespace mvgcuda {
 
@@ -65,6 +66,13 @@ struct alignas(16) KnnItem {
   int pad0, pad1, pad2;
 };
 
+struct RescanMeta {  // written by plan_rescan_kernel (second pass planned on the device)
+  int n_items;   // work items of the second knn2_kernel launch
+  int total;     // ambiguous queries of the batch
+  int overflow;  // total > cap: nothing was planned, the host re-runs the batch through its bounded multi-round path
+  int n_jobs;
+};
+
 struct KnnSmem {
   alignas(1024) uint8_t a[kSlotsA][kBytesA];
   alignas(1024) uint8_t b[kStagesB][kStageBytes];
@@ -84,6 +92,7 @@ struct KnnParams {
   const int* __restrict__ qcol;        // K1 layout for the rows the QUERY tensor map addresses (== ccol, except rescans)
   const KnnItem* __restrict__ items;   // [n_items]
   int n_items;
+  const RescanMeta* __restrict__ meta; // non-null: the item count lives on the device (meta->n_items), n_items is ignored
   KnnRecord* __restrict__ out;
   // Ratio-aware pruning (see slice_commit): the fp32 squared ratio of the Lowe test the records feed, or FLT_MAX when the
   // caller needs the exact 2nd neighbour of EVERY query (array-level API, ratio > 1 with the tie fix-up).
@@ -104,9 +113,11 @@ constexpr int kK1Rows = kHalfCols;  // rows per block of K1
 
 __global__ void __launch_bounds__(8 * kK1Rows)
 row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img_row0, const int* __restrict__ img_rows,
-                  int n_images, int arena_rows, int* __restrict__ ccol) {
+                  int n_images, int arena_rows, int row_begin /* multiple of 256: first arena row of this launch */,
+                  int* __restrict__ ccol) {
   __shared__ int norms[kK1Rows];
-  const int row = blockIdx.x * kK1Rows + (threadIdx.x >> 3);  // arena_rows is a multiple of 256
+  const int block_row0 = row_begin + blockIdx.x * kK1Rows;
+  const int row = block_row0 + (threadIdx.x >> 3);
   const int part = threadIdx.x & 7;
   const uint4 v = *reinterpret_cast<const uint4*>(arena + (size_t)row * kDim + part * 16);
   unsigned s = 0;
@@ -134,13 +145,13 @@ row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img
     int m = norms[threadIdx.x * kChunk];
 #pragma unroll
     for (int k = 1; k < kChunk; ++k) m = min(m, norms[threadIdx.x * kChunk + k]);
-    const int row0 = blockIdx.x * kK1Rows + threadIdx.x * kChunk;
+    const int row0 = block_row0 + threadIdx.x * kChunk;
     ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = m;
     // minimum of the block's 128 rows (8 chunk minima live in the first 8 lanes of warp 0)
     m = min(m, __shfl_xor_sync(0xffu, m, 1));
     m = min(m, __shfl_xor_sync(0xffu, m, 2));
     m = min(m, __shfl_xor_sync(0xffu, m, 4));
-    if (threadIdx.x == 0) ccol[static_cast<size_t>(arena_rows / kTileDb) * kTileC + blockIdx.x] = m;
+    if (threadIdx.x == 0) ccol[static_cast<size_t>(arena_rows / kTileDb) * kTileC + block_row0 / kK1Rows] = m;
   }
 }
 
@@ -150,7 +161,8 @@ row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img
 // longer than the whole item for images of ~2,000 rows).
 __global__ void __launch_bounds__(256)
 build_items_kernel(const PairJob* __restrict__ jobs, const int* __restrict__ item_start, int n_jobs, int n_items,
-                   KnnItem* __restrict__ items) {
+                   const RescanMeta* __restrict__ meta, KnnItem* __restrict__ items) {
+  if (meta) { n_jobs = meta->n_jobs; n_items = meta->n_items; }  // counts that only the device knows
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= n_items) return;
   int lo = 0, hi = n_jobs - 1;
@@ -285,6 +297,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
   const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader: issues the MMAs of the pair
   const int worker = static_cast<int>(blockIdx.x >> 1);
   const int n_workers = static_cast<int>(gridDim.x >> 1);
+  const int n_items = p.meta ? p.meta->n_items : p.n_items;
   const uint32_t sbase = ptx::smem_u32(&s);
 
   if (warp == 0 && lane == 0) {
@@ -315,7 +328,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     uint32_t a_it = 0;
     uint32_t sb = 0, b_par = 1;  // B ring position; parity to wait for on b_empty (a fresh barrier passes a wait on parity 1)
     uint32_t sc = 0, c_par = 1;  // constants ring, same
-    for (int item = worker; item < p.n_items; item += n_workers, ++a_it) {
+    for (int item = worker; item < n_items; item += n_workers, ++a_it) {
       const int4 it = *reinterpret_cast<const int4*>(&p.items[item]);  // db_row0, db_rows, q_row0, q_valid
       const uint32_t sa = a_it & 1u;
       ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, a_empty) + 8u * sa, ((a_it >> 1) & 1u) ^ 1u);
@@ -374,7 +387,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       uint32_t a_it = 0;
       uint32_t sb = 0, b_par = 0;  // B ring position; parity to wait for on b_full
       uint32_t eph = 0x3u;         // bit (t & 1): parity to wait for on acc_empty of buffer 2 (t & 1) + h (fresh barriers pass parity 1)
-      for (int item = worker; item < p.n_items; item += n_workers, ++a_it) {
+      for (int item = worker; item < n_items; item += n_workers, ++a_it) {
         const int db_rows = p.items[item].db_rows;
         const uint32_t sa = a_it & 1u;
         ptx::mbar_wait_addr(sb_ + offsetof(KnnSmem, a_full) + 8u * sa, (a_it >> 1) & 1u);
@@ -421,7 +434,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
     ptx::sts32(bound0, kTInit);
     ptx::sts32(bound0 + 4u * kBlockQ, kTInit);
     asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * kEpiParts) : "memory");
-    for (int item = worker; item < p.n_items; item += n_workers, ++item_it) {
+    for (int item = worker; item < n_items; item += n_workers, ++item_it) {
       const int4 it = *reinterpret_cast<const int4*>(&p.items[item]);  // db_row0, db_rows, q_row0, q_valid
       const int out_off = p.items[item].out_off;
       const int q_local = kBlockQ * static_cast<int>(rank) + row;
@@ -546,12 +559,16 @@ __global__ void __launch_bounds__(128, 1) i8_peak_probe_kernel(int iters) {
 // transiently and never change which small rows end up in S and T, so the machine is run over
 // rows {0,1} U {v : d[v] <= D2} only.  One warp per query; distances are recomputed on the CUDA
 // cores with __dp4a, which also makes this an independent check of the tensor-core path.
+// One launch for a whole batch: blockIdx.y = job, blockIdx.x = group of 8 queries of it.  q_arena is where the query rows
+// live (the image arena, or the scratch arena of the array-level API).
 __global__ void __launch_bounds__(256)
-tie_fixup_kernel(const uint8_t* __restrict__ arena, const PairJob J, KnnRecord* __restrict__ knn) {
+tie_fixup_kernel(const uint8_t* __restrict__ arena, const uint8_t* __restrict__ q_arena, const PairJob* __restrict__ jobs,
+                 int job0, KnnRecord* __restrict__ knn) {
+  const PairJob J = jobs[job0 + blockIdx.y];
   const int q = static_cast<int>((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (q >= J.q_rows) return;
-  const uint4* qp = reinterpret_cast<const uint4*>(arena + (size_t)(J.q_row0 + q) * kDim);
+  if (!J.valid || q >= J.q_rows) return;
+  const uint4* qp = reinterpret_cast<const uint4*>(q_arena + (size_t)(J.q_row0 + q) * kDim);
   uint4 qv[8];
   unsigned qn = 0;
 #pragma unroll
@@ -789,6 +806,165 @@ dedup_scatter_kernel(const PairJob* __restrict__ jobs, const int2* __restrict__ 
     if (keep) matches[out + rank] = m;
     out += tot;
   }
+}
+
+// ------------------------------------------------------------------------------------------ second pass, planned on the device
+// The host never learns how many queries are ambiguous (that would be a device->host round trip and a stream
+// synchronisation per batch): ONE CTA turns the per-pair counts of flag_ambiguous_kernel into the work lists of the second
+// pass.  Consecutive pairs against the same db image (the normal case, the pair list is (i, j)-ordered) share ONE job, so
+// their few flagged queries fill 256-query items together instead of one nearly empty item per pair.
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, total via reference
+__device__ __forceinline__ int block_scan_1024(int v, int* warp_sum /*[32] smem*/, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  __syncthreads();  // previous use of warp_sum finished
+  if (lane == 31) warp_sum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += y;
+    }
+    warp_sum[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  total = warp_sum[31];
+  return (warp ? warp_sum[warp - 1] : 0) + (x - v);
+}
+
+__global__ void __launch_bounds__(1024)
+plan_rescan_kernel(const PairJob* __restrict__ jobs, const int* __restrict__ resc_cnt, int nb, int cap,
+                   RescanSrc* __restrict__ rsrc, PairJob* __restrict__ rjobs, int* __restrict__ ritem_start,
+                   int* __restrict__ used /*[nb + 1] scratch*/, int* __restrict__ job_of /*[nb] scratch*/,
+                   RescanMeta* __restrict__ meta) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  // (A) position of every pair's flagged queries in the gathered buffer
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nb; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const int v = i < nb ? resc_cnt[i] : 0;
+    int tot;
+    const int ex = block_scan_1024(v, warp_sum, tot);
+    const int carry = carry_s;
+    if (i < nb) used[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  const int total = carry_s;
+  const bool overflow = total > cap;
+  if (threadIdx.x == 0) used[nb] = total;
+  __syncthreads();
+  // gather / scatter sources (one per pair; empty when the pass is skipped)
+  for (int i = threadIdx.x; i < nb; i += 1024) {
+    const PairJob J = jobs[i];
+    RescanSrc r;
+    r.src_out_off = J.out_off; r.src_q_row0 = J.q_row0; r.first = 0;
+    r.count = overflow ? 0 : resc_cnt[i];
+    r.dst_row0 = used[i];
+    rsrc[i] = r;
+  }
+  if (overflow || total == 0) {
+    if (threadIdx.x == 0) { meta->n_items = 0; meta->total = total; meta->overflow = overflow ? 1 : 0; meta->n_jobs = 0; }
+    return;
+  }
+  // (B) jobs = maximal runs of adjacent pairs against the same db image
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nb; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    int head = 0;
+    if (i < nb) head = (i == 0 || jobs[i].db_row0 != jobs[i - 1].db_row0 || jobs[i].db_rows != jobs[i - 1].db_rows) ? 1 : 0;
+    int tot;
+    const int ex = block_scan_1024(head, warp_sum, tot);
+    const int carry = carry_s;
+    if (i < nb) {
+      const int j = carry + ex + head - 1;  // job of pair i
+      job_of[i] = j;
+      if (head) {
+        PairJob R = jobs[i];
+        R.q_row0 = used[i];
+        R.out_off = used[i];
+        R.q_rows = 0;  // filled in below
+        R.valid = 1;
+        rjobs[j] = R;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  const int n_rj = carry_s;
+  __syncthreads();
+  // rows of a job = start of the next job (or the total) - its own start: the LAST pair of every run knows the end
+  for (int i = threadIdx.x; i < nb; i += 1024)
+    if (i == nb - 1 || job_of[i + 1] != job_of[i]) rjobs[job_of[i]].q_rows = used[i + 1] - rjobs[job_of[i]].q_row0;
+  __syncthreads();
+  // (C) work items per job
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n_rj; j0 += 1024) {
+    const int j = j0 + threadIdx.x;
+    const int v = j < n_rj ? (rjobs[j].q_rows + 2 * kBlockQ - 1) / (2 * kBlockQ) : 0;
+    int tot;
+    const int ex = block_scan_1024(v, warp_sum, tot);
+    const int carry = carry_s;
+    if (j < n_rj) ritem_start[j] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ritem_start[n_rj] = carry_s;
+    meta->n_items = carry_s; meta->total = total; meta->overflow = 0; meta->n_jobs = n_rj;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ row 13 on the GPU
+// IndexedMatchDecorator<float>::getDeduplicated (indexed_match_decorator.h:90-104): one thread per pair builds the
+// red-black tree the reference's std::set would build (rbtree_dedup.cuh) over the pair's matches, keyed by the (x, y) of
+// the LEFT feature, and writes the survivors in set order.  feats: [arena rows] (x, y) of every descriptor row; nodes:
+// scratch, [matches of the batch + pairs of the batch] (every pair needs one header node).
+__global__ void __launch_bounds__(64)
+dedup_xy_kernel(const PairJob* __restrict__ jobs, int nb, const int2* __restrict__ matches, const long long* __restrict__ offsets,
+                const int* __restrict__ counts, const float2* __restrict__ feats, RbNode* __restrict__ nodes,
+                int* __restrict__ order /*[matches of the batch]*/, int2* __restrict__ out, int* __restrict__ counts2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nb) return;
+  const int n = counts[p];
+  const long long off = offsets[p];
+  if (n == 0) { counts2[p] = 0; return; }
+  const int db_row0 = jobs[p].db_row0;
+  RbNode* nd = nodes + off + p;
+  const int2* m = matches + off;
+  for (int k = 0; k < n; ++k) {
+    const float2 f = feats[db_row0 + m[k].x];
+    nd[k].x = f.x;
+    nd[k].y = f.y;
+  }
+  int* ord = order + off;
+  const int kept = rbtree_dedup(nd, n, ord);
+  int2* o = out + off;
+  for (int k = 0; k < kept; ++k) o[k] = m[ord[k]];
+  counts2[p] = kept;
+}
+
+// Close the gaps the de-dup left: pair p's kept matches move from src[old_off[p] ..] to dst[new_off[p] ..].
+__global__ void __launch_bounds__(kCompactThreads)
+compact_pairs_kernel(const int2* __restrict__ src, const long long* __restrict__ old_off, const long long* __restrict__ new_off,
+                     const int* __restrict__ counts2, int2* __restrict__ dst) {
+  const int n = counts2[blockIdx.x];
+  const long long so = old_off[blockIdx.x], d0 = new_off[blockIdx.x];
+  for (int k = threadIdx.x; k < n; k += kCompactThreads) dst[d0 + k] = src[so + k];
 }
 
 }  // namespace mvgcuda

@@ -65,6 +65,7 @@ _ctx = C.c_void_p
 ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_version": (C.c_int, []),
     "mvgcuda_device_count": (C.c_int, []),
+    "mvgcuda_device_ordinal": (C.c_int, [C.c_int]),
     "mvgcuda_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),
     "mvgcuda_destroy": (None, [_ctx]),
     "mvgcuda_last_error": (C.c_char_p, [_ctx]),
@@ -72,6 +73,15 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_set_tuning": (C.c_int, [_ctx, C.c_float, C.c_int]),
     "mvgcuda_upload_images": (C.c_int, [_ctx, C.c_int, _u8pp, _i32p, C.c_int]),
     "mvgcuda_clone_images": (C.c_int, [_ctx, _ctx]),
+    "mvgcuda_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mvgcuda_host_free": (None, [C.c_void_p]),
+    "mvgcuda_stream_begin": (C.c_int, [_ctx, C.c_int, _i32p]),
+    "mvgcuda_stream_image": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_uint8), _f32p]),
+    "mvgcuda_stream_end": (C.c_int, [_ctx]),
+    "mvgcuda_db_create": (C.c_int, [_ctx, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_void_p)]),
+    "mvgcuda_db_destroy": (None, [_ctx, C.c_void_p]),
+    "mvgcuda_db_rows": (C.c_int, [C.c_void_p]),
+    "mvgcuda_db_knn2": (C.c_int, [_ctx, C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, _i32p, _f32p]),
     "mvgcuda_num_images": (C.c_int, [_ctx]),
     "mvgcuda_image_rows": (C.c_int, [_ctx, C.c_int]),
     "mvgcuda_knn2": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _i32p, _f32p]),
@@ -138,7 +148,7 @@ class PairMatches:
 
     def pair(self, p: int) -> np.ndarray:
         """[count][2] (_i, _j) of pair p."""
-        return self.matches[self.offsets[p]:self.offsets[p + 1]]
+        return self.matches[self.offsets[p]:self.offsets[p] + self.counts[p]]
 
     def as_dict(self) -> Dict[Tuple[int, int], np.ndarray]:
         """PairWiseMatches (indexed_match.h:69): first insertion wins for duplicate keys, as std::map::insert."""
@@ -159,7 +169,6 @@ class Context:
             raise MvgCudaError(f"mvgcuda_create({device}) failed [{rc}]: {self._lib.mvgcuda_last_error(None).decode()}")
         self._h = h
         self.device = device
-        self._rows: List[int] = []
 
     # -- plumbing
     def close(self) -> None:
@@ -212,7 +221,6 @@ class Context:
             ptrs[k] = m.ctypes.data_as(C.POINTER(C.c_uint8)) if m.shape[0] else None
             rows[k] = m.shape[0]
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rows, int(pinned)), "mvgcuda_upload_images")
-        self._rows = [m.shape[0] for m in mats]
 
     def upload_images_device(self, device_ptrs: Sequence[int], rows: Sequence[int]) -> None:
         """Same as upload_images, from descriptor arrays that already live in device memory (raw CUDA pointers, e.g.
@@ -224,7 +232,25 @@ class Context:
             ptrs[k] = C.cast(C.c_void_p(int(device_ptrs[k])), C.POINTER(C.c_uint8)) if rows[k] else None
             rws[k] = int(rows[k])
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rws, 0), "mvgcuda_upload_images")
-        self._rows = [int(r) for r in rows]
+
+    def stream_images(self, descs: Sequence[np.ndarray], feats_xy: Optional[Sequence[np.ndarray]] = None,
+                      order: Optional[Sequence[int]] = None) -> None:
+        """Same residency as upload_images (+ set_features), through the streaming entry points: one asynchronous copy per
+        image, in `order` (default 0..n-1), then one wait."""
+        mats = [_as_u8_matrix(d) if len(d) else np.zeros((0, DIM), np.uint8) for d in descs]
+        n = len(mats)
+        rows = (C.c_int32 * max(n, 1))(*[m.shape[0] for m in mats])
+        self._check(self._lib.mvgcuda_stream_begin(self._h, n, rows), "mvgcuda_stream_begin")
+        fm = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy] if feats_xy is not None else None
+        for k in (order if order is not None else range(n)):
+            m = mats[k]
+            dp = m.ctypes.data_as(C.POINTER(C.c_uint8)) if m.shape[0] else None
+            fp = fm[k].ctypes.data_as(_f32p) if fm is not None and m.shape[0] else None
+            self._check(self._lib.mvgcuda_stream_image(self._h, int(k), dp, fp), "mvgcuda_stream_image")
+        self._check(self._lib.mvgcuda_stream_end(self._h), "mvgcuda_stream_end")
+
+    def db_create(self, db: np.ndarray) -> "ResidentDb":
+        return ResidentDb(self, db)
 
     def clone_images_from(self, src: "Context") -> None:
         """Replica of another context's uploaded collection (and features), copied device to device."""
@@ -242,7 +268,7 @@ class Context:
 
     # -- array level
     def knn2(self, db_img: int, q_img: int, tie_mode: int = TIE_REFERENCE) -> Tuple[np.ndarray, np.ndarray]:
-        nq = self._rows[q_img] if 0 <= q_img < len(self._rows) else 0
+        nq = max(self._lib.mvgcuda_image_rows(self._h, q_img), 0)  # the library's own count: valid for clones and streamed sets too
         idx = np.empty((max(nq, 1), 2), np.int32)
         dist = np.empty((max(nq, 1), 2), np.float32)
         self._check(self._lib.mvgcuda_knn2(self._h, db_img, q_img, tie_mode, idx.ctypes.data_as(_i32p),
@@ -290,6 +316,38 @@ class Context:
         self._check(self._lib.mvgcuda_export_matches(self._h, pairs.ctypes.data_as(_i32p), path.encode()), "mvgcuda_export_matches")
 
 
+class ResidentDb:
+    """A database image that stays in HBM (mvgcuda_db_*): Build once, search many times, only the queries travel."""
+
+    def __init__(self, ctx: Context, db: np.ndarray):
+        self._ctx = ctx
+        db = _as_u8_matrix(db)
+        h = C.c_void_p()
+        ctx._check(ctx._lib.mvgcuda_db_create(ctx._h, db.ctypes.data_as(C.POINTER(C.c_uint8)), db.shape[0], C.byref(h)), "mvgcuda_db_create")
+        self._h = h
+        self.rows = db.shape[0]
+
+    def knn2(self, query: np.ndarray, tie_mode: int = TIE_REFERENCE) -> Tuple[np.ndarray, np.ndarray]:
+        query = _as_u8_matrix(query)
+        nq = query.shape[0]
+        idx = np.empty((max(nq, 1), 2), np.int32)
+        dist = np.empty((max(nq, 1), 2), np.float32)
+        self._ctx._check(self._ctx._lib.mvgcuda_db_knn2(self._ctx._h, self._h, query.ctypes.data_as(C.POINTER(C.c_uint8)), nq, tie_mode,
+                                                        idx.ctypes.data_as(_i32p), dist.ctypes.data_as(_f32p)), "mvgcuda_db_knn2")
+        return idx[:nq], dist[:nq]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._ctx._lib.mvgcuda_db_destroy(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 # Mirrors of the reference's operator interfaces (same names / argument meaning / error behaviour)
 
@@ -305,34 +363,40 @@ class ArrayMatcherCuda:
 
     def __init__(self, ctx: Optional[Context] = None, tie_mode: int = TIE_REFERENCE):
         self._ctx = ctx or Context(0)
-        self._db: Optional[np.ndarray] = None
+        self._db: Optional[ResidentDb] = None
+        self._rows = 0
         self._tie = tie_mode
 
     def Build(self, dataset: np.ndarray, rows_num: int, dimension: int = DIM) -> bool:
-        if rows_num < 1:  # matcher_brute_force.h:43-46
+        if self._db is not None:
+            self._db.close()
             self._db = None
+        self._rows = 0
+        if rows_num < 1:  # matcher_brute_force.h:43-46
             return False
         if dimension != DIM:
             raise ValueError("ArrayMatcherCuda handles 128-byte descriptors only")
-        self._db = _as_u8_matrix(np.asarray(dataset).reshape(-1, DIM)[:rows_num]).copy()
+        db = _as_u8_matrix(np.asarray(dataset).reshape(-1, DIM)[:rows_num])
+        self._rows = db.shape[0]
+        if self._rows == 1:  # k == 1 against a single row: duplicate it so the 2-NN kernel has two candidates
+            db = np.concatenate([db, db], axis=0)
+        self._db = self._ctx.db_create(db)  # the rows go to HBM once; searches upload only their queries
         return True
 
     def SearchNeighbours(self, query: np.ndarray, query_num: int, vec_indice: list, vec_distance: list,
                          nearest_neighbor_num: int = 2) -> bool:
-        rows = 0 if self._db is None else self._db.shape[0]
-        if nearest_neighbor_num > rows or query_num < 1:
+        if nearest_neighbor_num > self._rows or query_num < 1:
             import sys
             print("Too much asked nearest neighbors", file=sys.stderr)
             return False
         if nearest_neighbor_num not in (1, 2):
             raise ValueError("ArrayMatcherCuda accelerates k = 1 or 2 only")
         q = _as_u8_matrix(np.asarray(query).reshape(-1, DIM)[:query_num])
-        db = self._db
-        if rows == 1:  # k == 1 against a single row: duplicate it so the 2-NN kernel has two candidates
-            db = np.concatenate([db, db], axis=0)
-        idx, dist = self._ctx.knn2_arrays(db, q, self._tie)
         k = nearest_neighbor_num
-        if rows == 1:
+        # k == 1: std::partial_sort(first, first + 1, last) keeps the FIRST minimum (strict < in __heap_select,
+        # indexed_sort.h:52-66), i.e. the lowest index; only k == 2 needs the two-slot tie machine
+        idx, dist = self._db.knn2(q, self._tie if k == 2 else TIE_LOWEST_INDEX)
+        if self._rows == 1:
             idx = np.zeros_like(idx)
         vec_indice.extend(idx[:, :k].reshape(-1).tolist())
         vec_distance.extend(dist[:, :k].reshape(-1).tolist())
@@ -342,9 +406,8 @@ class ArrayMatcherCuda:
         """Single nearest neighbour (matcher_brute_force.h:61-89: std::min_element => lowest index on ties)."""
         if self._db is None:
             return False, -1, 0.0
-        db = self._db if self._db.shape[0] > 1 else np.concatenate([self._db, self._db], axis=0)
-        idx, dist = self._ctx.knn2_arrays(db, _as_u8_matrix(np.asarray(query).reshape(1, DIM)), TIE_LOWEST_INDEX)
-        return True, (int(idx[0, 0]) if self._db.shape[0] > 1 else 0), float(dist[0, 0])
+        idx, dist = self._db.knn2(_as_u8_matrix(np.asarray(query).reshape(1, DIM)), TIE_LOWEST_INDEX)
+        return True, (int(idx[0, 0]) if self._rows > 1 else 0), float(dist[0, 0])
 
 
 class MatcherCudaAllInMemory:

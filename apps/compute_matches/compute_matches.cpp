@@ -1,5 +1,5 @@
 // compute_matches (putative-matching stage) -- the reference's apps/compute_matches/compute_matches.cpp:47-248 with
-// the CUDA back-end and a multi-GPU pair scheduler.  Same flags, defaults, files and resume rules:
+// the CUDA back-end and a streaming multi-GPU pair scheduler.  Same flags, defaults, files and resume rules:
 //
 //   -i/--imadir <dir>  -o/--outdir <dir>  [-r/--distratio 0.6]  [-s/--isZoom 0]  [-p/--contrastThreshold 0.04]
 //   [-g/--geometricModel f|e|h]            (compute_matches.cpp:51-68; spellings of cmd_line.h:80-97:
@@ -11,7 +11,17 @@
 // <outdir>/matches.putative.txt byte-identical to PairedIndexedMatchToStream (indexed_match_utils.h:22-38) of the
 // reference's BRUTE-FORCE matcher (the typedef at compute_matches.cpp:226-227; the shipped default :222-223 is the
 // approximate, randomised FLANN kd-tree and is deliberately not reproduced).
-// Resume rule kept: if matches.putative.txt exists, matching is skipped (compute_matches.cpp:230-234).
+// Resume rule kept: if matches.putative.txt exists it is imported (pairedIndexedMatchImport, indexed_match_utils.h:48-73)
+// and matching is skipped (compute_matches.cpp:230-234).
+//
+// Scheduler (what replaces MatcherAllInMemory::LoadData + Match, matcher_all_in_memory.h:44-141):
+//   1. the .desc headers are scanned for the row counts, then one context per GPU is created, all concurrently;
+//   2. loader threads (all host cores) parse one image each -- binary .desc straight into page-locked staging, text .feat
+//      -- and hand it to EVERY GPU at once (mvgcuda_stream_image: asynchronous copy + norms kernel), so files are still
+//      being parsed while earlier images travel; each GPU keeps a full replica (<= ~1 GB), there is no collective;
+//   3. the i < j pair list is cut into contiguous, cost-balanced (rows_i * rows_j) shards, one per GPU; every GPU runs
+//      rows 7-13 of the path on its shard (mvgcuda_match_collection; batches pipelined inside the library);
+//   4. the text of every shard is formatted concurrently and written in pair order.
 // Out of scope of this build: SIFT extraction (the stage before: .feat/.desc must exist) and
 // the AC-RANSAC geometric filter (the stage after: run the reference's own binary on the exported file).
 #include <algorithm>
@@ -21,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -33,7 +44,7 @@
 namespace {
 
 struct Options {
-  std::string imadir, outdir, geometric_model = "f";
+  std::string imadir, outdir, geometric_model = "e";  // compute_matches.cpp:58
   float dist_ratio = 0.6f;   // compute_matches.cpp:55
   bool is_zoom = false;
   float contrast_threshold = 0.04f;
@@ -130,6 +141,54 @@ inline void append_uint(std::string& out, unsigned long long v) {
   while (n) out.push_back(tmp[--n]);
 }
 
+// rows of a .desc file from its header and size, without reading the payload (0 for a missing / empty file; -1 malformed)
+int desc_rows_from_header(const std::string& path, int& header_bytes) {
+  header_bytes = 0;
+  std::ifstream f(path.c_str(), std::ios::binary | std::ios::ate);
+  if (!f.is_open()) return 0;
+  const std::streamoff size = f.tellg();
+  if (size == 0) return 0;
+  f.seekg(0);
+  unsigned char h[8] = {0};
+  f.read(reinterpret_cast<char*>(h), std::min<std::streamoff>(8, size));
+  for (int hdr : {8, 4}) {  // sizeof(size_t) of the writer: 8 on Linux x86-64, 4 in the shipped data/et files
+    if (size < hdr) continue;
+    uint64_t n = 0;
+    memcpy(&n, h, hdr);
+    if ((uint64_t)size == (uint64_t)hdr + n * MVGCUDA_DIM) { header_bytes = hdr; return (int)n; }
+  }
+  return -1;
+}
+
+// pairedIndexedMatchImport (indexed_match_utils.h:48-73): "i j\ncount\n" + count x "_i _j\n" until the first token that
+// does not parse; a key seen twice keeps its LAST block (operator[] assignment).  Returns false if the file cannot be opened.
+struct ImportedMatches {
+  std::vector<std::pair<std::pair<size_t, size_t>, std::vector<std::pair<int, int> > > > blocks;  // file order
+  size_t pairs = 0, matches = 0;  // after the map semantics (distinct keys, last block wins)
+};
+bool import_matches(const std::string& path, ImportedMatches& out) {
+  std::ifstream in(path.c_str());
+  if (!in.is_open()) {
+    std::cout << std::endl << "ERROR IndexedMatchesUtils::import(...)" << std::endl << "with : " << path << std::endl;
+    return false;
+  }
+  size_t l, r, number;
+  while (in >> l >> r >> number) {
+    std::vector<std::pair<int, int> > m(number);
+    for (size_t k = 0; k < number; ++k) in >> m[k].first >> m[k].second;
+    out.blocks.push_back(std::make_pair(std::make_pair(l, r), m));
+  }
+  std::vector<size_t> order(out.blocks.size());
+  for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return out.blocks[a].first < out.blocks[b].first; });
+  for (size_t k = 0; k < order.size(); ++k) {
+    if (k + 1 < order.size() && out.blocks[order[k + 1]].first == out.blocks[order[k]].first) continue;  // a later block of the key wins
+    ++out.pairs;
+    out.matches += out.blocks[order[k]].second.size();
+  }
+  return true;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -165,61 +224,135 @@ int main(int argc, char** argv) {
   }
   const std::string putative = opt.outdir + "/matches.putative.txt";
   if (file_exists(putative)) {  // compute_matches.cpp:230-234
-    std::cout << "\nPREVIOUS RESULTS LOADED: " << putative << " exists, putative matching skipped" << std::endl;
+    ImportedMatches im;
+    if (!import_matches(putative, im)) return EXIT_FAILURE;
+    std::cout << std::endl << "PUTATIVE MATCHES -- PREVIOUS RESULTS LOADED" << std::endl
+              << im.pairs << " pairs, " << im.matches << " putative matches imported from " << putative << "; matching skipped" << std::endl;
     return EXIT_SUCCESS;
   }
 
+  typedef std::chrono::steady_clock Clock;
+  auto ms = [](Clock::time_point a_, Clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a_).count(); };
+  const Clock::time_point t_begin = Clock::now();
   const int n = (int)names.size();
-  std::vector<std::vector<uint8_t> > desc(n);
-  std::vector<std::vector<float> > xy(n);
+  const int64_t n_pairs = (int64_t)n * (n - 1) / 2;
+  // ---- 1. header scan (row counts), then one context per GPU, created concurrently
   std::vector<int32_t> rows(n, 0);
-  auto t0 = std::chrono::steady_clock::now();
-  {
-    // one image per task over the host cores: the .feat text parse dominates (4 floats per feature)
-    std::atomic<int> next(0), first_missing(n), first_bad(n);
-    auto load = [&]() {
-      for (int i = next++; i < n; i = next++) {
-        const std::string base = opt.outdir + "/" + basename_part(names[i]);
-        if (!file_exists(base + ".feat") || !file_exists(base + ".desc")) {
-          int cur = first_missing.load();
-          while (i < cur && !first_missing.compare_exchange_weak(cur, i)) {}
-          continue;
-        }
-        int drows = 0;
-        if (!load_desc(base + ".desc", desc[i], drows) || !load_feat_xy(base + ".feat", xy[i])) {
-          int cur = first_bad.load();
-          while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
-          continue;
-        }
-        rows[i] = (int32_t)std::min<size_t>(xy[i].size() / 2, (size_t)drows);  // row count from the features (matcher_all_in_memory.h:80)
-        xy[i].resize(2 * (size_t)rows[i]);
-      }
-    };
-    const int n_threads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::max(n, 1)));
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) pool.emplace_back(load);
-    for (auto& t : pool) t.join();
-    if (first_missing.load() < n) {
-      const std::string base = opt.outdir + "/" + basename_part(names[first_missing.load()]);
+  std::vector<int> hdr_bytes(n, 0);
+  for (int i = 0; i < n; ++i) {
+    const std::string base = opt.outdir + "/" + basename_part(names[i]);
+    if (!file_exists(base + ".feat") || !file_exists(base + ".desc")) {
       std::cerr << "missing " << base << ".feat/.desc: SIFT extraction (compute_matches.cpp:188-216) is outside this build; "
                 << "run the reference's extraction stage first" << std::endl;
       return EXIT_FAILURE;
     }
-    if (first_bad.load() < n) {
-      std::cerr << "cannot parse " << opt.outdir << "/" << basename_part(names[first_bad.load()]) << ".feat/.desc" << std::endl;
-      return EXIT_FAILURE;
-    }
+    const int r = desc_rows_from_header(base + ".desc", hdr_bytes[i]);
+    if (r < 0) { std::cerr << "cannot parse " << base << ".desc" << std::endl; return EXIT_FAILURE; }
+    rows[i] = r;
   }
-  std::vector<int32_t> pairs;
-  for (int i = 0; i < n; ++i)
-    for (int j = i + 1; j < n; ++j) { pairs.push_back(i); pairs.push_back(j); }
-  const int64_t n_pairs = (int64_t)pairs.size() / 2;
-
-  int gpus = opt.gpus > 0 ? opt.gpus : mvgcuda_device_count();
-  if (gpus < 1) { std::cerr << "no sm_100 CUDA device visible (there is no CPU fallback)" << std::endl; return EXIT_FAILURE; }
-  gpus = (int)std::max<int64_t>(1, std::min<int64_t>(gpus, n_pairs));
+  const int n_devices = mvgcuda_device_count();
+  if (n_devices < 1) { std::cerr << "no sm_100 CUDA device visible (there is no CPU fallback)" << std::endl; return EXIT_FAILURE; }
+  int gpus = opt.gpus > 0 ? opt.gpus : n_devices;  // more shards than devices: they share devices round-robin
+  gpus = (int)std::max<int64_t>(1, std::min<int64_t>(gpus, std::max<int64_t>(n_pairs, 1)));
+  std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
+  std::vector<std::string> ctx_error(gpus);
+  auto destroy_all = [&]() { for (mvgcuda_ctx* c : ctxs) if (c) mvgcuda_destroy(c); };
+  {
+    std::vector<std::thread> creators;
+    for (int g = 0; g < gpus; ++g)
+      creators.emplace_back([&, g]() {
+        // shard g runs on the g-th sm_100 device of the box (CUDA ordinals need not be 0..N-1 on a mixed box)
+        if (mvgcuda_create(std::max(0, mvgcuda_device_ordinal(g % n_devices)), &ctxs[g]) != MVGCUDA_OK) ctx_error[g] = mvgcuda_last_error(NULL);
+      });
+    for (auto& t : creators) t.join();
+  }
+  for (int g = 0; g < gpus; ++g)
+    if (!ctx_error[g].empty()) { std::cerr << "GPU " << g << ": " << ctx_error[g] << std::endl; destroy_all(); return EXIT_FAILURE; }
+  const Clock::time_point t_ctx = Clock::now();
   std::cout << std::endl << " - PUTATIVE MATCHES - " << n << " images, " << n_pairs << " pairs, " << gpus << " GPU(s)" << std::endl;
 
+  // ---- 2. streaming load: parse -> page-locked staging -> every GPU
+  for (int g = 0; g < gpus; ++g)
+    if (mvgcuda_stream_begin(ctxs[g], n, rows.data()) != MVGCUDA_OK) {
+      std::cerr << "GPU " << g << ": " << mvgcuda_last_error(ctxs[g]) << std::endl;
+      destroy_all();
+      return EXIT_FAILURE;
+    }
+  std::vector<void*> staging(n, (void*)NULL);  // per image: [rows][128] u8 then [rows][2] float, page-locked; freed after stream_end
+  std::vector<std::mutex> ctx_mtx(gpus);
+  std::atomic<int> next(0), first_bad(n), mismatch(0);
+  std::string stream_error;
+  std::mutex err_mtx;
+  auto load = [&]() {
+    for (int i = next++; i < n; i = next++) {
+      const std::string base = opt.outdir + "/" + basename_part(names[i]);
+      const size_t nrows = (size_t)rows[i];
+      uint8_t* d = NULL;
+      float* xy = NULL;
+      if (nrows) {
+        if (mvgcuda_host_alloc(nrows * (MVGCUDA_DIM + 2 * sizeof(float)), &staging[i]) != MVGCUDA_OK) { first_bad = std::min(first_bad.load(), i); continue; }
+        d = static_cast<uint8_t*>(staging[i]);
+        xy = reinterpret_cast<float*>(d + nrows * MVGCUDA_DIM);
+        std::ifstream f((base + ".desc").c_str(), std::ios::binary);
+        f.seekg(hdr_bytes[i]);
+        f.read(reinterpret_cast<char*>(d), (std::streamsize)(nrows * MVGCUDA_DIM));
+        if ((size_t)f.gcount() != nrows * MVGCUDA_DIM) { first_bad = std::min(first_bad.load(), i); continue; }
+      }
+      // .feat: x y scale orientation per line (feature.h:117-133); the row count of the pair comes from the features in
+      // the reference (matcher_all_in_memory.h:80) -- the streaming layout assumes it equals the .desc count
+      size_t got = 0;
+      {
+        std::ifstream f((base + ".feat").c_str());
+        float x, y, sc, o;
+        while (f >> x >> y >> sc >> o) {
+          if (got < nrows) { xy[2 * got] = x; xy[2 * got + 1] = y; }
+          ++got;
+        }
+        if (f.bad()) { first_bad = std::min(first_bad.load(), i); continue; }
+      }
+      if (got != nrows) { ++mismatch; continue; }
+      for (int g = 0; g < gpus; ++g) {
+        std::lock_guard<std::mutex> lk(ctx_mtx[g]);
+        if (mvgcuda_stream_image(ctxs[g], i, d, xy) != MVGCUDA_OK) {
+          std::lock_guard<std::mutex> el(err_mtx);
+          if (stream_error.empty()) stream_error = std::string("GPU ") + std::to_string(g) + ": " + mvgcuda_last_error(ctxs[g]);
+        }
+      }
+    }
+  };
+  {
+    const int n_threads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::max(n, 1)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(load);
+    for (auto& t : pool) t.join();
+  }
+  auto free_staging = [&]() { for (void* p_ : staging) if (p_) mvgcuda_host_free(p_); };
+  bool stream_ok = stream_error.empty() && first_bad.load() >= n && mismatch.load() == 0;
+  for (int g = 0; g < gpus && stream_ok; ++g)
+    if (mvgcuda_stream_end(ctxs[g]) != MVGCUDA_OK) { stream_error = mvgcuda_last_error(ctxs[g]); stream_ok = false; }
+  if (first_bad.load() < n) {
+    std::cerr << "cannot parse " << opt.outdir << "/" << basename_part(names[first_bad.load()]) << ".feat/.desc" << std::endl;
+    for (int g = 0; g < gpus; ++g) mvgcuda_stream_end(ctxs[g]);
+    free_staging(); destroy_all();
+    return EXIT_FAILURE;
+  }
+  if (!stream_error.empty()) { std::cerr << stream_error << std::endl; free_staging(); destroy_all(); return EXIT_FAILURE; }
+  if (mismatch.load() > 0) {
+    // a .feat with a different row count than its .desc: the reference takes the count from the features and reads past /
+    // short of the descriptors; refused here rather than reproduced
+    std::cerr << mismatch.load() << " image(s) whose .feat and .desc row counts differ: refused (the reference over-/under-reads here)" << std::endl;
+    for (int g = 0; g < gpus; ++g) mvgcuda_stream_end(ctxs[g]);
+    free_staging(); destroy_all();
+    return EXIT_FAILURE;
+  }
+  free_staging();
+  const Clock::time_point t_load = Clock::now();
+
+  // ---- 3. pair shards
+  std::vector<int32_t> pairs;
+  pairs.reserve((size_t)n_pairs * 2);
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) { pairs.push_back(i); pairs.push_back(j); }
   const float ratio_sq = opt.dist_ratio * opt.dist_ratio;  // Square(float), numeric.h:108-111: rounded in fp32
   std::vector<int64_t> bounds(gpus + 1, n_pairs);
   {
@@ -230,39 +363,32 @@ int main(int argc, char** argv) {
     for (int g = 1; g < gpus; ++g) bounds[g] = std::lower_bound(csum.begin(), csum.end(), csum[n_pairs] * g / gpus) - csum.begin();
     for (int g = 1; g <= gpus; ++g) bounds[g] = std::max(bounds[g], bounds[g - 1]);
   }
-  std::vector<const uint8_t*> dptr(n);
-  std::vector<const float*> fptr(n);
-  for (int i = 0; i < n; ++i) { dptr[i] = rows[i] ? desc[i].data() : NULL; fptr[i] = xy[i].data(); }
-
-  struct Shard { std::vector<int32_t> counts; std::vector<int32_t> matches; std::string error; float gpu_ms = 0; };
+  struct Shard { std::vector<int32_t> counts; std::vector<int32_t> matches; std::string error; float gpu_ms = 0; std::string text; long long total = 0; };
   std::vector<Shard> shards(gpus);
-  auto t1 = std::chrono::steady_clock::now();
-  // GPU 0 reads the collection over PCIe once; every other GPU takes a replica of its arena device to device
-  // (NVLink / NVSwitch), then all match their shard of the pair list concurrently -- no collective afterwards
-  std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
-  auto destroy_all = [&]() { for (mvgcuda_ctx* c : ctxs) if (c) mvgcuda_destroy(c); };
-  if (mvgcuda_create(0, &ctxs[0]) != MVGCUDA_OK) { std::cerr << "GPU 0: " << mvgcuda_last_error(NULL) << std::endl; return EXIT_FAILURE; }
-  if (mvgcuda_upload_images(ctxs[0], n, dptr.data(), rows.data(), 0) != MVGCUDA_OK ||
-      mvgcuda_set_features(ctxs[0], n, fptr.data(), rows.data()) != MVGCUDA_OK) {
-    std::cerr << "GPU 0: " << mvgcuda_last_error(ctxs[0]) << std::endl;
-    destroy_all();
-    return EXIT_FAILURE;
-  }
   auto work = [&](int g) {
     Shard& S = shards[g];
-    if (g > 0) {
-      if (mvgcuda_create(g, &ctxs[g]) != MVGCUDA_OK) { S.error = mvgcuda_last_error(NULL); return; }
-      if (mvgcuda_clone_images(ctxs[g], ctxs[0]) != MVGCUDA_OK) { S.error = mvgcuda_last_error(ctxs[g]); return; }
-    }
-    mvgcuda_ctx* ctx = ctxs[g];
     const int64_t b = bounds[g], e = bounds[g + 1];
     mvgcuda_pair_matches pm;
-    if (mvgcuda_match_collection(ctx, e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
-      S.error = mvgcuda_last_error(ctx);
-    } else {
-      S.counts.assign(pm.counts, pm.counts + (e - b));
-      S.matches.assign(pm.matches, pm.matches + 2 * pm.offsets[e - b]);
-      S.gpu_ms = pm.gpu_ms;
+    if (mvgcuda_match_collection(ctxs[g], e - b, pairs.data() + 2 * b, ratio_sq, 0, &pm) != MVGCUDA_OK) {
+      S.error = mvgcuda_last_error(ctxs[g]);
+      return;
+    }
+    S.gpu_ms = pm.gpu_ms;
+    // the text of the shard, straight from the library's result buffers (pairs are in lexicographic (i, j) order ==
+    // std::map iteration order)
+    std::string& out = S.text;
+    out.reserve((size_t)pm.offsets[e - b] * 12 + (size_t)(e - b) * 16 + 64);
+    for (int64_t p = b; p < e; ++p) {
+      const int c = pm.counts[p - b];
+      const int32_t* m = pm.matches + 2 * pm.offsets[p - b];
+      append_uint(out, (unsigned)pairs[2 * p]); out.push_back(' ');
+      append_uint(out, (unsigned)pairs[2 * p + 1]); out.push_back('\n');
+      append_uint(out, (unsigned)c); out.push_back('\n');
+      for (int k = 0; k < c; ++k) {
+        append_uint(out, (unsigned)m[2 * k]); out.push_back(' ');
+        append_uint(out, (unsigned)m[2 * k + 1]); out.push_back('\n');
+      }
+      S.total += c;
     }
   };
   {
@@ -270,52 +396,28 @@ int main(int argc, char** argv) {
     for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
     for (auto& t : th) t.join();
   }
-  destroy_all();  // only after every replica has been taken
-  auto t2 = std::chrono::steady_clock::now();
+  const Clock::time_point t_match = Clock::now();
   for (int g = 0; g < gpus; ++g)
-    if (!shards[g].error.empty()) { std::cerr << "GPU " << g << ": " << shards[g].error << std::endl; return EXIT_FAILURE; }
+    if (!shards[g].error.empty()) { std::cerr << "GPU " << g << ": " << shards[g].error << std::endl; destroy_all(); return EXIT_FAILURE; }
 
-  // export: pairs are generated in lexicographic (i,j) order == std::map iteration order
+  // ---- 4. export in shard (== pair) order
   FILE* f = fopen(putative.c_str(), "wb");
-  if (!f) { std::cerr << "cannot write " << putative << std::endl; return EXIT_FAILURE; }
+  if (!f) { std::cerr << "cannot write " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
   long long total = 0;
-  {
-    // text of every shard formatted concurrently, written in shard (== pair) order
-    std::vector<std::string> text(gpus);
-    std::vector<long long> shard_total(gpus, 0);
-    auto format = [&](int g) {
-      const Shard& S = shards[g];
-      std::string& out = text[g];
-      out.reserve(S.matches.size() * 6 + (size_t)(bounds[g + 1] - bounds[g]) * 16 + 64);
-      size_t off = 0;
-      for (int64_t p = bounds[g]; p < bounds[g + 1]; ++p) {
-        const int c = S.counts[p - bounds[g]];
-        append_uint(out, (unsigned)pairs[2 * p]); out.push_back(' ');
-        append_uint(out, (unsigned)pairs[2 * p + 1]); out.push_back('\n');
-        append_uint(out, (unsigned)c); out.push_back('\n');
-        for (int k = 0; k < c; ++k, ++off) {
-          append_uint(out, (unsigned)S.matches[2 * off]); out.push_back(' ');
-          append_uint(out, (unsigned)S.matches[2 * off + 1]); out.push_back('\n');
-        }
-        shard_total[g] += c;
-      }
-    };
-    std::vector<std::thread> th;
-    for (int g = 0; g < gpus; ++g) th.emplace_back(format, g);
-    for (auto& t : th) t.join();
-    for (int g = 0; g < gpus; ++g) {
-      fwrite(text[g].data(), 1, text[g].size(), f);
-      total += shard_total[g];
-    }
+  bool ok = true;
+  for (int g = 0; g < gpus; ++g) {
+    ok = ok && fwrite(shards[g].text.data(), 1, shards[g].text.size(), f) == shards[g].text.size();
+    total += shards[g].total;
   }
-  if (fclose(f) != 0) { std::cerr << "short write to " << putative << std::endl; return EXIT_FAILURE; }
-  auto t3 = std::chrono::steady_clock::now();
-  auto ms = [](std::chrono::steady_clock::time_point a_, std::chrono::steady_clock::time_point b_) {
-    return std::chrono::duration<double, std::milli>(b_ - a_).count();
-  };
-  std::cout << "loaded in " << ms(t0, t1) << " ms; matched " << n_pairs << " pairs (" << total << " putative matches) in " << ms(t1, t2)
-            << " ms on " << gpus << " GPU(s) (" << (n_pairs / std::max(1e-9, ms(t1, t2) * 1e-3)) << " pairs/s incl. upload + host de-dup); exported in "
-            << ms(t2, t3) << " ms -> " << putative << std::endl;
+  if (fclose(f) != 0 || !ok) { std::cerr << "short write to " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
+  const Clock::time_point t_export = Clock::now();
+  destroy_all();
+  float gpu_ms_max = 0;
+  for (int g = 0; g < gpus; ++g) gpu_ms_max = std::max(gpu_ms_max, shards[g].gpu_ms);
+  std::cout << "start-up (contexts + headers) " << ms(t_begin, t_ctx) << " ms; load (parse + upload to " << gpus << " GPU(s)) " << ms(t_ctx, t_load)
+            << " ms; match + format " << ms(t_load, t_match) << " ms (GPU time " << gpu_ms_max << " ms, " << n_pairs << " pairs, " << total
+            << " putative matches, " << (n_pairs / std::max(1e-9, ms(t_load, t_match) * 1e-3)) << " pairs/s); export " << ms(t_match, t_export)
+            << " ms -> " << putative << std::endl;
   std::cout << "geometric filtering (-g " << opt.geometric_model << ") is the next stage and is not part of this build" << std::endl;
   return EXIT_SUCCESS;
 }

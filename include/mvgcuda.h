@@ -17,7 +17,7 @@
  *   export           PairedIndexedMatchToStream  indexed_match_utils.h:22-38
  *
  * Conventions: plain C symbols, every function returns an int status (0 = MVGCUDA_OK), no
- * exception crosses the boundary, all buffers are caller-owned unless stated, a context is
+ * exception crosses the boundary (every entry point catches: std::bad_alloc -> MVGCUDA_ERR_NOMEM), all buffers are caller-owned unless stated, a context is
  * bound to ONE GPU and may be used from one host thread at a time (use one context per GPU).
  * Descriptors are dense row-major [rows][128] uint8 (== std::vector<Descriptor<uchar,128>>,
  * descriptor.h:23-58).  There is no CPU fallback: without a CUDA device every compute entry
@@ -59,6 +59,9 @@ int mvgcuda_version(void);
 
 /* Number of visible CUDA devices with compute capability 10.x (0 if none / no driver). */
 int mvgcuda_device_count(void);
+/* CUDA ordinal of the k-th such device (k = 0 .. count-1), -1 if there is none: what to pass to mvgcuda_create when
+ * the box mixes GPU generations or the sm_100 devices are not ordinals 0..N-1. */
+int mvgcuda_device_ordinal(int k);
 
 /* Create a context on CUDA device `device`.  Fails (MVGCUDA_ERR_CUDA) unless it is sm_100. */
 int mvgcuda_create(int device, mvgcuda_ctx** out);
@@ -76,11 +79,9 @@ int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
 /* Tuning of the ratio-aware pruning of the pair / collection level (results never depend on it).
  * prune_rho in (0, 1]: a query that currently fails the ratio test only admits db rows with d <= prune_rho * d(best);
  * 1 = plain best-distance bound (no query is ever matched twice), default 0.8.  It is clamped from below to the ratio
- * of the call.  rescan_rows: rows of the buffer the ambiguous queries are gathered into per round (0 = default 2^20). */
+ * of the call.  rescan_rows: rows of the buffer the ambiguous queries of a batch are gathered into (0 = default 2^20);
+ * a batch with more of them is matched again through a bounded multi-round path (same results, one synchronisation). */
 int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows);
-/* The kernel has two epilogue schedules with identical results ("inplace", "deferred"); the library picks one per batch
- * from the db image size.  Environment variable MVGCUDA_EPILOGUE=inplace|deferred (read by mvgcuda_create) forces one;
- * the parity tests run under both. */
 
 /* ------------------------------------------------------------------------------------------
  * Residency: copy n_images descriptor arrays into the context's HBM arena (replaces the
@@ -98,6 +99,21 @@ int mvgcuda_upload_images(mvgcuda_ctx* ctx, int n_images, const uint8_t* const* 
  * collection over PCIe once per GPU.  `src` must have finished its upload and must not upload or be destroyed meanwhile;
  * it may be matching.  Replaces any image set of `ctx`. */
 int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src);
+
+/* Streaming form of the upload, for a loader that parses files while earlier images already travel
+ * (apps/compute_matches: the reference loads every file before matching, matcher_all_in_memory.h:44-60):
+ *   stream_begin  lays out the arena for n_images images of the given row counts (replaces any previous set);
+ *   stream_image  enqueues the copy of ONE image's descriptors ([rows][128] u8) and, optionally, its feature
+ *                 coordinates ([rows][2] float, NULL = none) plus the per-row constants kernel for its rows -- it does
+ *                 not wait, so the buffers (page-locked for a truly asynchronous copy) must stay untouched until
+ *                 stream_end or the next synchronising call; images may arrive in any order, each exactly once;
+ *   stream_end    waits for every copy.  Matching calls are stream-ordered after the copies even without it. */
+/* Page-locked host memory for the staging buffers of stream_image (usable by every GPU of the box). */
+int mvgcuda_host_alloc(size_t bytes, void** out);
+void mvgcuda_host_free(void* p);
+int mvgcuda_stream_begin(mvgcuda_ctx* ctx, int n_images, const int32_t* rows);
+int mvgcuda_stream_image(mvgcuda_ctx* ctx, int image, const uint8_t* desc, const float* feats_xy);
+int mvgcuda_stream_end(mvgcuda_ctx* ctx);
 int mvgcuda_num_images(const mvgcuda_ctx* ctx);
 int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image); /* <0 on bad id */
 
@@ -114,6 +130,17 @@ int mvgcuda_knn2(mvgcuda_ctx* ctx, int db_img, int q_img, int tie_mode, int32_t*
  * context, the uploaded image set is left untouched). */
 int mvgcuda_knn2_arrays(mvgcuda_ctx* ctx, const uint8_t* db, int db_rows, const uint8_t* query,
                         int q_rows, int tie_mode, int32_t* idx, float* dist);
+
+/* A database that stays in HBM == ArrayMatcherBruteForce::Build (matcher_brute_force.h:42-50; the reference borrows the
+ * caller's pointer, this COPIES the rows to the GPU once) followed by any number of SearchNeighbours calls, each of
+ * which uploads only its queries.  rows >= 1 (db_knn2 needs rows >= 2 like mvgcuda_knn2).  A db belongs to the context
+ * it was created on; calls on one context are serialised by the caller. */
+typedef struct mvgcuda_db mvgcuda_db;
+int mvgcuda_db_create(mvgcuda_ctx* ctx, const uint8_t* db, int rows, mvgcuda_db** out);
+void mvgcuda_db_destroy(mvgcuda_ctx* ctx, mvgcuda_db* db);
+int mvgcuda_db_rows(const mvgcuda_db* db);
+int mvgcuda_db_knn2(mvgcuda_ctx* ctx, const mvgcuda_db* db, const uint8_t* query, int q_rows, int tie_mode,
+                    int32_t* idx, float* dist);
 
 /* ------------------------------------------------------------------------------------------
  * Pair level: for each pair (I=pairs[2p], J=pairs[2p+1]) run, on the GPU,
@@ -155,11 +182,13 @@ int mvgcuda_match_pairs(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs,
 /* ------------------------------------------------------------------------------------------
  * Collection level == MatcherAllInMemory<KeypointSet<ScalePointFeature,Descriptor<uchar,128>>,
  * ArrayMatcherBruteForce<...>>::Match  (matcher_all_in_memory.h:62-141) restricted to the given
- * pair list: match_pairs as above, then on a host worker pool the coordinate de-duplication
- * IndexedMatchDecorator<float>::getDeduplicated (indexed_match_decorator.h:33-53,90-104; same
- * comparator, same std::set) using the features' (x,y).  feats_xy[i] is [rows_i][2] float
- * (x,y of ScalePointFeature, feature.h:79-113) for every uploaded image.
- * Result layout as for match_pairs (order within a pair is the std::set iteration order). */
+ * pair list: match_pairs as above, then the coordinate de-duplication
+ * IndexedMatchDecorator<float>::getDeduplicated (indexed_match_decorator.h:33-53,90-104) using the features' (x,y) --
+ * on the GPU, one thread per pair building the red-black tree libstdc++'s std::set would build (the reference's
+ * comparator is not a strict weak order, so the container's algorithm defines the result).  feats_xy[i] is
+ * [rows_i][2] float (x,y of ScalePointFeature, feature.h:79-113) for every uploaded image; they are copied to HBM.
+ * Result layout as for match_pairs (order within a pair is the std::set iteration order).
+ * host_threads is ignored (before version 200 the de-duplication ran on a host pool). */
 int mvgcuda_set_features(mvgcuda_ctx* ctx, int n_images, const float* const* feats_xy,
                          const int32_t* rows);
 int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pairs,

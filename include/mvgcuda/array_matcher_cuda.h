@@ -10,13 +10,16 @@
 //
 // Behaviour kept from the BF matcher:
 //   * Build(ptr, rows, dim): false if rows < 1 (matcher_brute_force.h:43-46).  Unlike BF, which borrows `ptr`
-//     (Eigen::Map, :47-48), the rows are COPIED (to the GPU at the first search), so the caller may free them.
+//     (Eigen::Map, :47-48), the rows are COPIED -- to HBM, once, by Build (mvgcuda_db_create); every search uploads only
+//     its queries -- so the caller may free them.
 //   * SearchNeighbours APPENDS k (index, distance) per query (push_back, :128-131); returns false and prints
 //     "Too much asked nearest neighbors" when k > rows or nq < 1 (:107-110); re-entrant after Build (the reference
 //     calls it from several OpenMP threads on one object, matcher_all_in_memory.h:84-107) -- calls are serialised
 //     on the context by a mutex.
 //   * DistanceType is float (Accumulator<unsigned char>::Type, metric.h:9-10).
 // Only k = 1 and k = 2 and dimension 128 are accelerated -- what the path uses (NNN__ = 2, matcher_all_in_memory.h:102).
+// Ties: k = 2 reproduces the two-slot machine std::partial_sort(first, first + 2, last) amounts to (indexed_sort.h:52-66);
+// k = 1 returns the FIRST minimum, as partial_sort(first, first + 1, last) does (strict < in __heap_select).
 // There is no CPU fallback: without a B200 the calls fail (return false) with the CUDA error on std::cerr.
 #ifndef MVGCUDA_ARRAY_MATCHER_CUDA_H_
 #define MVGCUDA_ARRAY_MATCHER_CUDA_H_
@@ -63,17 +66,36 @@ class ArrayMatcherCuda : public ArrayMatcher<Scalar, Metric> {
   typedef typename Metric::ResultType DistanceType;
 
   explicit ArrayMatcherCuda(int device = 0, int tie_mode = MVGCUDA_TIE_REFERENCE) : device_(device), tie_mode_(tie_mode) {}
-  virtual ~ArrayMatcherCuda() {}
+  virtual ~ArrayMatcherCuda() { Release(); }
+  ArrayMatcherCuda(const ArrayMatcherCuda&) = delete;
+  ArrayMatcherCuda& operator=(const ArrayMatcherCuda&) = delete;
 
   bool Build(const Scalar* dataset, int rows_num, int dimension) {
-    db_.clear();
-    rows_ = 0;
+    Release();
     if (rows_num < 1) return false;
     if (dimension != MVGCUDA_DIM) {
       std::cerr << "ArrayMatcherCuda: dimension must be " << MVGCUDA_DIM << std::endl;
       return false;
     }
-    db_.assign(reinterpret_cast<const uint8_t*>(dataset), reinterpret_cast<const uint8_t*>(dataset) + (size_t)rows_num * dimension);
+    std::mutex* mtx = NULL;
+    mvgcuda_ctx* ctx = MvgCudaContextPool::get(device_, &mtx);
+    if (!ctx) return false;
+    const uint8_t* rows = reinterpret_cast<const uint8_t*>(dataset);
+    // the 2-NN kernel needs two db rows; a single-row db (k == 1 only) is kept as two copies of that row
+    std::vector<uint8_t> twice;
+    int n = rows_num;
+    if (rows_num == 1) {
+      twice.assign(rows, rows + MVGCUDA_DIM);
+      twice.insert(twice.end(), rows, rows + MVGCUDA_DIM);
+      rows = twice.data();
+      n = 2;
+    }
+    std::lock_guard<std::mutex> lock(*mtx);
+    if (mvgcuda_db_create(ctx, rows, n, &db_) != MVGCUDA_OK) {
+      std::cerr << "mvgcuda: " << mvgcuda_last_error(ctx) << std::endl;
+      db_ = NULL;
+      return false;
+    }
     rows_ = rows_num;
     return true;
   }
@@ -99,30 +121,35 @@ class ArrayMatcherCuda : public ArrayMatcher<Scalar, Metric> {
       std::cerr << "ArrayMatcherCuda: only 1 or 2 nearest neighbours are supported" << std::endl;
       return false;
     }
-    return Search(query, query_num, vec_indice, vec_distance, (int)nearest_neighbor_num, tie_mode_);
+    // k == 1: partial_sort(first, first + 1, last) keeps the first minimum, i.e. the lowest index
+    return Search(query, query_num, vec_indice, vec_distance, (int)nearest_neighbor_num,
+                  nearest_neighbor_num == 1 ? (int)MVGCUDA_TIE_LOWEST_INDEX : tie_mode_);
   }
 
  private:
+  void Release() {
+    if (db_) {
+      std::mutex* mtx = NULL;
+      mvgcuda_ctx* ctx = MvgCudaContextPool::get(device_, &mtx);
+      if (ctx) {
+        std::lock_guard<std::mutex> lock(*mtx);
+        mvgcuda_db_destroy(ctx, db_);
+      }
+      db_ = NULL;
+    }
+    rows_ = 0;
+  }
+
   bool Search(const Scalar* query, int nq, std::vector<int>* vi, std::vector<DistanceType>* vd, int k, int tie) {
     std::mutex* mtx = NULL;
     mvgcuda_ctx* ctx = MvgCudaContextPool::get(device_, &mtx);
-    if (!ctx) return false;
-    // the 2-NN kernel needs two db rows; a single-row db (k == 1 only) is searched as two copies of that row
-    std::vector<uint8_t> twice;
-    const uint8_t* db = db_.data();
-    int rows = rows_;
-    if (rows == 1) {
-      twice = db_;
-      twice.insert(twice.end(), db_.begin(), db_.end());
-      db = twice.data();
-      rows = 2;
-    }
+    if (!ctx || !db_) return false;
     std::vector<int32_t> idx(2 * (size_t)nq);
     std::vector<float> dist(2 * (size_t)nq);
     int rc;
     {
-      std::lock_guard<std::mutex> lock(*mtx);
-      rc = mvgcuda_knn2_arrays(ctx, db, rows, reinterpret_cast<const uint8_t*>(query), nq, tie, idx.data(), dist.data());
+      std::lock_guard<std::mutex> lock(*mtx);  // re-entrant after Build, like the reference (matcher_all_in_memory.h:84-107)
+      rc = mvgcuda_db_knn2(ctx, db_, reinterpret_cast<const uint8_t*>(query), nq, tie, idx.data(), dist.data());
       if (rc != MVGCUDA_OK) std::cerr << "mvgcuda: " << mvgcuda_last_error(ctx) << std::endl;
     }
     if (rc != MVGCUDA_OK) return false;
@@ -135,7 +162,7 @@ class ArrayMatcherCuda : public ArrayMatcher<Scalar, Metric> {
   }
 
   int device_, tie_mode_;
-  std::vector<uint8_t> db_;
+  mvgcuda_db* db_ = NULL;
   int rows_ = 0;
 };
 

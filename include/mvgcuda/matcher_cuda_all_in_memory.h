@@ -6,13 +6,14 @@
 // (matcher_all_in_memory.h:19-147); replaces `MatcherAllInMemory<KeypointSetT, MatcherT> collectionMatcher(ratio)`
 // at apps/compute_matches/compute_matches.cpp:237 one-for-one.  Match() uploads every descriptor array once,
 // shards the i<j pair list over `n_gpus` contexts (one host thread per GPU, no collective: pairs are independent),
-// runs rows 7-12 of the path on the GPUs and the coordinate de-duplication (IndexedMatchDecorator, row 13) on a host
-// pool inside libmvgcuda, and inserts EVERY pair -- empty ones included (matcher_all_in_memory.h:135) -- into the map.
+// runs rows 7-13 of the path (incl. the coordinate de-duplication of IndexedMatchDecorator) on the GPUs,
+// and inserts EVERY pair -- empty ones included (matcher_all_in_memory.h:135) -- into the map.
 // Documented deviation: images with fewer than 2 descriptors yield empty pairs where the reference has undefined
 // behaviour (null Eigen::Map).
 #ifndef MVGCUDA_MATCHER_CUDA_ALL_IN_MEMORY_H_
 #define MVGCUDA_MATCHER_CUDA_ALL_IN_MEMORY_H_
 
+#include <algorithm>
 #include <iostream>
 #include <map>
 #include <string>
@@ -88,7 +89,8 @@ class MatcherCudaAllInMemory : public Matcher {
     std::vector<std::string> errors(gpus);
     // GPU 0 reads the collection over PCIe; the other GPUs take a replica of its arena device to device (NVLink)
     std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
-    if (mvgcuda_create(0, &ctxs[0]) != MVGCUDA_OK) {
+    // shard g runs on the g-th sm_100 device of the box (CUDA ordinals need not be 0..N-1 on a mixed box)
+    if (mvgcuda_create(std::max(0, mvgcuda_device_ordinal(0)), &ctxs[0]) != MVGCUDA_OK) {
       errors[0] = mvgcuda_last_error(NULL);
     } else if (mvgcuda_upload_images(ctxs[0], n, desc.data(), rows.data(), 0) != MVGCUDA_OK ||
                mvgcuda_set_features(ctxs[0], n, xy.data(), rows.data()) != MVGCUDA_OK) {
@@ -96,7 +98,7 @@ class MatcherCudaAllInMemory : public Matcher {
     }
     auto work = [&](int g) {
       if (g > 0) {
-        if (mvgcuda_create(g, &ctxs[g]) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(NULL); return; }
+        if (mvgcuda_create(std::max(0, mvgcuda_device_ordinal(g)), &ctxs[g]) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(NULL); return; }
         if (mvgcuda_clone_images(ctxs[g], ctxs[0]) != MVGCUDA_OK) { errors[g] = mvgcuda_last_error(ctxs[g]); return; }
       }
       mvgcuda_ctx* ctx = ctxs[g];

@@ -75,8 +75,32 @@ static void array_level(int db_rows, int nq, int alphabet, unsigned seed) {
   if (i0 != i1) std::cerr << "  array_level(" << db_rows << "," << nq << "," << alphabet << ") indices differ" << std::endl;
 }
 
+// k = 1 under heavy ties (tiny alphabet, duplicated rows): ArrayMatcherBruteForce runs partial_sort(first, first + 1, last),
+// which keeps the FIRST minimum; and the reference's usage pattern Build once / search many times (matcher_all_in_memory.h:84-107)
+static void array_level_k1_and_reuse(int db_rows, int nq, int alphabet, unsigned seed) {
+  std::vector<unsigned char> db = rnd(db_rows, alphabet, seed);
+  for (int r = 1; r < db_rows; r += 3) std::copy(db.begin(), db.begin() + 128, db.begin() + (size_t)r * 128);  // many exact duplicates
+  MatcherBF ref;
+  ArrayMatcherCuda<unsigned char, MetricT> gpu;
+  CHECK(ref.Build(db.data(), db_rows, 128) == gpu.Build(db.data(), db_rows, 128));
+  for (int round = 0; round < 3; ++round) {  // the db stays in HBM: three searches, one upload of it
+    std::vector<unsigned char> q = rnd(nq, alphabet, seed + 10 + round);
+    std::copy(db.begin(), db.begin() + 128, q.begin());  // a query equal to the duplicated row: distance-0 ties
+    for (size_t k : {size_t(1), size_t(2)}) {
+      std::vector<int> i0, i1;
+      std::vector<float> d0, d1;
+      CHECK(ref.SearchNeighbours(q.data(), nq, &i0, &d0, k) == gpu.SearchNeighbours(q.data(), nq, &i1, &d1, k));
+      CHECK(d0 == d1);
+      CHECK(i0 == i1);
+      if (i0 != i1) std::cerr << "  k=" << k << " round " << round << ": indices differ under ties" << std::endl;
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   // array level: random, tie-heavy, degenerate
+  array_level_k1_and_reuse(600, 300, 2, 31);
+  array_level_k1_and_reuse(257, 129, 3, 32);
   array_level(300, 200, 256, 1);
   array_level(1000, 513, 3, 2);
   array_level(2, 5, 2, 3);

@@ -1,17 +1,23 @@
-// CPU check of experiments/rbtree_dedup.h against the real container the reference uses:
-// std::set<DecoratedMatch, DecoratedLess> range-constructed (indexed_match_decorator.h:90-104), libstdc++.
+// CPU check of 3dreconstruction_b200/csrc/rbtree_dedup.cuh (the product's device code, compiled for the host here) against the
+// real container the reference uses: std::set range-constructed with the reference's FULL ordering predicate over
+// (x1, y1, x2, y2) (indexed_match_decorator.h:33-53, 90-104), libstdc++.
 #include <cstdio>
 #include <cstdlib>
 #include <random>
 #include <set>
 #include <vector>
 
-#include "../../experiments/rbtree_dedup.h"
+#include "../../3dreconstruction_b200/csrc/rbtree_dedup.cuh"
 
-using mvgcuda::DecoratedKey;
-
-struct Elem { DecoratedKey k; int pos; };
-struct Less { bool operator()(const Elem& a, const Elem& b) const { return mvgcuda::decorated_less(a.k, b.k); } };
+struct Elem { float x1, y1, x2, y2; int pos; };
+struct Less {  // the reference's predicate, expression by expression
+  bool operator()(const Elem& a, const Elem& b) const {
+    if (a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2) return false;
+    if (a.x1 < b.x1) return a.y1 < b.y1;
+    else if (a.x1 > b.x1) return a.y1 < b.y1;
+    return a.x1 < b.x1;
+  }
+};
 
 int main(int argc, char** argv) {
   const int cases = argc > 1 ? atoi(argv[1]) : 20000;
@@ -21,19 +27,20 @@ int main(int argc, char** argv) {
     const int n = (c % 50 == 0) ? (int)(rng() % 3000) : (int)(rng() % 120);
     const int alpha = 2 + (int)(rng() % (c % 3 == 0 ? 6 : 400));  // small alphabets: many equal x / y / (x, y)
     std::vector<Elem> v(n);
-    std::vector<DecoratedKey> keys(n);
     for (int i = 0; i < n; ++i) {
-      DecoratedKey k;
-      k.x1 = (float)(rng() % alpha) * 0.5f; k.y1 = (float)(rng() % alpha) * 0.25f;
-      k.x2 = (float)(rng() % alpha); k.y2 = (float)(rng() % alpha);
-      if (i > 0 && rng() % 9 == 0) k = keys[rng() % i];           // exact duplicates
-      keys[i] = k;
-      v[i] = Elem{k, i};
+      Elem e;
+      e.x1 = (float)(rng() % alpha) * 0.5f; e.y1 = (float)(rng() % alpha) * 0.25f;
+      e.x2 = (float)(rng() % alpha); e.y2 = (float)(rng() % alpha);
+      if (i > 0 && rng() % 9 == 0) { const int src = rng() % i; e = v[src]; }  // exact duplicates
+      if (c % 97 == 0 && rng() % 40 == 0) e.x1 = std::nanf("");               // unordered keys
+      e.pos = i;
+      v[i] = e;
     }
     std::set<Elem, Less> s(v.begin(), v.end());
-    std::vector<int> parent(n + 1), left(n + 1), right(n + 1), out(n + 1);
-    std::vector<unsigned char> red(n + 1);
-    const int m = mvgcuda::rbtree_dedup(keys.data(), n, parent.data(), left.data(), right.data(), red.data(), out.data());
+    std::vector<mvgcuda::RbNode> nd(n + 1);
+    std::vector<int> out(n + 1);
+    for (int i = 0; i < n; ++i) { nd[i].x = v[i].x1; nd[i].y = v[i].y1; }
+    const int m = mvgcuda::rbtree_dedup(nd.data(), n, out.data());
     if (m != (int)s.size()) { printf("case %d: size %d != %zu\n", c, m, s.size()); return 1; }
     int q = 0;
     for (const Elem& e : s) {

@@ -119,7 +119,7 @@ def test_shard_world2_gloo(tmp_path):
 
 
 def test_rbtree_dedup_restatement_matches_std_set(tmp_path):
-    """experiments/rbtree_dedup.h (device-compatible restatement of libstdc++'s std::set range construction for the
+    """3dreconstruction_b200/csrc/rbtree_dedup.cuh (the device code of row 13, compiled for the host: restatement of libstdc++'s std::set range construction for the
     reference's non-strict-weak coordinate comparator, SURVEY 8(a) row 13) against the real std::set, on the CPU."""
     import shutil
     import subprocess
