@@ -520,14 +520,16 @@ static int compact_batch(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S, float r
     CU_CHECK(ctx, ctx->d_nodes.reserve(nrec + nb + 1));
     CU_CHECK(ctx, ctx->d_order.reserve(nrec));
     // survivors of pair p land in d_tmp at the pair's old offset, then move to their final (dense) place
-    dedup_xy_kernel<<<(nb + 63) / 64, 64, 0, st>>>(S.d_jobs.p, nb, matches1, offsets1, counts1, A.feat.p, ctx->d_nodes.p, ctx->d_order.p,
-                                                  ctx->d_tmp.p, S.d_counts.p);
+    dedup_xy_smem_kernel<<<nb, 32, 0, st>>>(S.d_jobs.p, matches1, offsets1, counts1, A.feat.p, ctx->d_tmp.p, S.d_counts.p);
+    CU_CHECK(ctx, cudaGetLastError());
+    dedup_xy_kernel<<<(nb + 63) / 64, 64, 0, st>>>(S.d_jobs.p, nb, kDedupSmemCap, matches1, offsets1, counts1, A.feat.p, ctx->d_nodes.p,
+                                                  ctx->d_order.p, ctx->d_tmp.p, S.d_counts.p);
     CU_CHECK(ctx, cudaGetLastError());
     scan_counts_kernel<<<1, 1024, 0, st>>>(S.d_counts.p, nb, 0, S.d_offsets.p, ctx->d_total.p + 1);
     CU_CHECK(ctx, cudaGetLastError());
     compact_pairs_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_tmp.p, offsets1, S.d_offsets.p, S.d_counts.p, S.d_matches.p);
     CU_CHECK(ctx, cudaGetLastError());
-    S.launches += 3;
+    S.launches += 4;
   }
   CU_CHECK(ctx, S.h_counts.reserve(nb));
   CU_CHECK(ctx, S.h_offsets.reserve(nb + 1));

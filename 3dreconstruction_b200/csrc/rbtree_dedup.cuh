@@ -23,11 +23,18 @@
 
 namespace mvgcuda {
 
-struct alignas(16) RbNode {  // 32 bytes: the descent reads one 16-byte half per level
+struct alignas(16) RbNode {  // global-memory form, 32 bytes: the descent reads one 16-byte half per level
+  static constexpr int kNil = -1;
   float x, y;                // (x1, y1) of the match's left feature
   int left, right;
   int parent, red;
   int pad0, pad1;
+};
+
+struct alignas(16) RbNode16 {  // shared-memory form, 16 bytes: pairs with fewer than 65,535 matches
+  static constexpr int kNil = 0xFFFF;
+  float x, y;
+  unsigned short left, right, parent, red;
 };
 
 MVG_HD bool decorated_less_xy(float ax, float ay, float bx, float by) {
@@ -37,8 +44,9 @@ MVG_HD bool decorated_less_xy(float ax, float ay, float bx, float by) {
 // nd[0 .. n-1]: node k is element k of the input with x / y already filled in; nd[n] is the header (parent = root,
 // left = leftmost, right = rightmost).  Writes the input positions of the surviving elements in set (in-order) order to
 // out[0 ..] and returns their number.
-MVG_HD int rbtree_dedup(RbNode* __restrict__ nd, int n, int* __restrict__ out) {
-  const int H = n, NIL = -1;
+template <typename Node, typename OutT>
+MVG_HD int rbtree_dedup(Node* __restrict__ nd, int n, OutT* __restrict__ out) {
+  const int H = n, NIL = Node::kNil;
   nd[H].parent = NIL; nd[H].left = H; nd[H].right = H; nd[H].red = 1;
   int count = 0;
 
@@ -158,7 +166,7 @@ MVG_HD int rbtree_dedup(RbNode* __restrict__ nd, int n, int* __restrict__ out) {
   if (count > 0) {
     int c = nd[H].left;
     while (c != H) {
-      out[m++] = c;
+      out[m++] = static_cast<OutT>(c);
       if (nd[c].right != NIL) {
         c = nd[c].right;
         while (nd[c].left != NIL) c = nd[c].left;

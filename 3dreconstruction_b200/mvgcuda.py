@@ -422,8 +422,7 @@ class MatcherCudaAllInMemory:
     def __init__(self, distRatio: float, ctx: Optional[Context] = None, host_threads: int = 0):
         self.distance_ratio = np.float32(distRatio)
         self._ctx = ctx or Context(0)
-        self._threads = host_threads
-        self._n = 0
+        self._n = 0  # (host_threads: accepted and ignored -- the coordinate de-dup runs on the GPU)
 
     def LoadArrays(self, descs: Sequence[np.ndarray], feats_xy: Sequence[np.ndarray]) -> bool:
         # row counts come from the features, as in the reference (matcher_all_in_memory.h:80,85,107)
@@ -434,8 +433,8 @@ class MatcherCudaAllInMemory:
             if d.shape[0] < r:
                 raise MvgCudaError(".feat has more rows than .desc (the reference over-reads here; refused)")
             d2.append(d[:r])
-        self._ctx.upload_images(d2)
-        self._ctx.set_features(feats_xy)
+        # one asynchronous copy per image (descriptors + coordinates) and one wait: the streaming entry points
+        self._ctx.stream_images(d2, feats_xy)
         self._n = len(d2)
         return True
 
@@ -452,7 +451,7 @@ class MatcherCudaAllInMemory:
         n = self._n if file_names is None else len(file_names)
         if pairs is None:
             pairs = pairs_exhaustive(n)
-        self.last = self._ctx.match_collection(pairs, float(square_f32(self.distance_ratio)), self._threads)
+        self.last = self._ctx.match_collection(pairs, float(square_f32(self.distance_ratio)))
         return self.last.as_dict()
 
     def Export(self, path: str) -> None:

@@ -1,21 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- image pairs/sec of exhaustive u8 SIFT-128 putative matching (BF squared-L2 2-NN + ratio test).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 Workload (BASELINE.json): 10,000 u8 SIFT-128 descriptors per image, exhaustive pairs, ratio 0.8.  At N=1 this is
-config 3 (100 images, 4,950 pairs).  For N>1 the pair list is sharded with no collective (pairs are independent);
-the collection grows as ~sqrt(N) (142 / 200 / 282 images) so that every GPU keeps ~4,950 pairs: weak scaling.
+config 3 (100 images, 4,950 pairs).  For N>1 the pair list is sharded with no collective (pairs are independent):
+  --scaling weak (default)  the collection grows as ~sqrt(N) (142 / 200 / 282 images) so that every GPU keeps ~4,950 pairs;
+  --scaling strong          BASELINE configs[2] as worded: the same 100 images / 4,950 pairs split over the N GPUs.
 Every rank holds a replica of the descriptor arena (the north star's pair scheduler).
 
 One "step" = one pass of the hot path over this rank's pair shard.
   value  whole-job pairs/s with descriptors already resident in HBM (device time, CUDA events, max over ranks)
   e2e    same metric through the public collection API (MatcherCudaAllInMemory mirror -> C ABI) from PINNED HOST
-         buffers: H2D of all descriptors + kernels + D2H of matches + host coordinate de-dup, every step
-  roofline       the fused tcgen05 kernel: algorithmic int8 ops (2*nI*nJ*128 per pair) / its CUDA-event time
+         buffers: H2D of all descriptors + coordinates, kernels (incl. the coordinate de-dup), D2H of the matches, every step
+  roofline       the fused tcgen05 kernel: algorithmic int8 ops (2*nI*nJ*128 per pair) / its CUDA-event time, against the
+                 int8 tensor rate MEASURED in this run (MMA-only probe, sustained for seconds under the clock sampler)
   cpu_baseline   the reference's own CPU brute-force code (oracle/_ref, built from /root/reference) on a bounded sample
+  checksum       order-independent digest of every pair's match list (sum of per-pair hashes mod 2^64, all-reduced), so runs
+                 at different N over the same pair set (--scaling strong) can be compared
 """
 import argparse
 import importlib
@@ -25,6 +29,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -34,15 +39,16 @@ sys.path.insert(0, ROOT)
 ROWS = 10000
 RATIO = 0.8
 PAIRS_PER_GPU = 4950
+CONFIG3_IMAGES = 100
 SYNTH_CONFIG = 3
 METRIC = "image pairs/sec, 10k u8 SIFT/img exhaustive BF-L2+ratio"
+NOMINAL_INT8_TOPS = 4500.0
 
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -67,18 +73,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
+    def window(self, t0, t1):
+        sm, mx, pw, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
+        for ts, line in list(self.lines):
             if ts < t0 or ts > t1 + 0.2:
                 continue
             f = [x.strip() for x in line.split(",")]
@@ -87,12 +85,24 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx = float(f[2])
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": float(np.median(pw)) if pw else None}
+
+    def stop(self):
+        if not self.proc:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
 
 
 def _dist_env():
@@ -102,34 +112,43 @@ def _dist_env():
     return rank, world, local
 
 
-def cpu_reference_run(nq=ROWS, flann=False):
+def cpu_reference_run(nq=ROWS, flann=False, threads=None):
     """Time the reference's own CPU path (oracle/_ref; the L1 port if it is absent): one (10k-row db, nq-query) unit per
-    host thread, nq <= 10000 (a full pair when nq == 10000; cost is linear in nq)."""
+    host thread, nq <= 10000 (a full pair when nq == 10000; cost is linear in nq).  threads=1: the reference's shipped
+    configuration (USE_OPENMP is defined nowhere in its tree); default: its OpenMP mode on every host core."""
     from oracle import oracle
     synth = importlib.import_module("3dreconstruction_b200.synth")
     pkg = importlib.import_module("3dreconstruction_b200")
     cores = os.cpu_count() or 1
+    threads = int(threads or cores)
     imgs = synth.collection(SYNTH_CONFIG, 4, ROWS)
     rs = float(pkg.square_f32(RATIO))
     use_ref = os.path.exists(oracle.L0_OMP_PATH)
-    n = max(1, min(cores, 512))
+    n = max(1, min(threads, 512))
     combos = [(a, b) for a in range(4) for b in range(4) if a != b]
     dbs = [imgs[combos[k % len(combos)][0]] for k in range(n)]
     qs = [imgs[combos[k % len(combos)][1]][:nq] for k in range(n)]
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ASSIGN (not setdefault), or the "all cores" arm runs on one thread
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     t0 = time.time()
     if use_ref:
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        oracle.L0(openmp=True).bench(dbs, qs, rs, flann=flann)
+        lib = oracle.L0(openmp=True)
+        try:
+            lib.lib.ref_set_threads(threads)
+        except AttributeError:
+            pass
+        lib.bench(dbs, qs, rs, flann=flann)
         kind = "reference"
     else:
         oracle.L1().bench_bf(dbs, qs, rs)
         kind = "port"
     dt = time.time() - t0
     pairs_equiv = n * nq / float(ROWS)
-    return {"value": pairs_equiv / dt, "unit": "pairs/s", "cores": cores, "kind": kind, "seconds": dt, "pairs_equiv": pairs_equiv,
+    return {"value": pairs_equiv / dt, "unit": "pairs/s", "cores": threads, "host_cores": cores, "kind": kind, "seconds": dt,
+            "pairs_equiv": pairs_equiv,
             "sample": f"{n} units of (10000-row db x {nq} queries) = {pairs_equiv:.2f} pairs of 10000x10000 u8 SIFT-128, "
                       f"{'FLANN kd-tree' if flann else 'brute force'} + ratio test, "
-                      f"{'reference code in its OpenMP mode (-DUSE_OPENMP), one unit per thread' if use_ref else 'oracle L1 port, OpenMP over queries'}"}
+                      f"{'reference code' if use_ref else 'oracle L1 port'} on {threads} thread(s), one unit per thread"}
 
 
 def run_reference(args):
@@ -149,16 +168,45 @@ def run_reference(args):
     r = runs[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32 (the reference accumulates exact integers in float, metric.h:51-82)", "data": "synthetic",
         "config": {"workload": f"bounded sample of BASELINE config 3 per step: {r['sample']}, ratio {RATIO}",
-                   "rows_per_image": ROWS, "ratio": RATIO},
+                   "rows_per_image": ROWS, "ratio": RATIO, "omp_threads": r["cores"], "host_cores": r["host_cores"]},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _pair_digest(pm, pairs, n):
+    """Order-independent digest of a result: sum over pairs of crc64-ish(i, j, matches) mod 2^64, and the match total."""
+    counts = np.ctypeslib.as_array(pm.counts, shape=(max(n, 1),))[:n]
+    offsets = np.ctypeslib.as_array(pm.offsets, shape=(n + 1,))
+    total = int(offsets[n])
+    matches = np.ctypeslib.as_array(pm.matches, shape=(max(total, 1) * 2,))
+    acc = 0
+    for p in range(n):
+        o, c = int(offsets[p]), int(counts[p])
+        blob = np.array(pairs[p], np.int32).tobytes() + matches[2 * o:2 * (o + c)].tobytes()
+        acc = (acc + ((zlib.crc32(blob) << 32) | zlib.adler32(blob))) & 0xFFFFFFFFFFFFFFFF
+    return acc, total
+
+
+def probe_int8(ctx, sampler, seconds=3.0):
+    """MMA-only int8 rate of this GPU: burst (best launch) and sustained (median of the launches of the last half of a
+    `seconds`-long back-to-back loop, clocks sampled meanwhile)."""
+    rates, stamps = [], []
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        ops, _ = ctx.probe_i8_peak(200000)
+        rates.append(ops / 1e12)
+        stamps.append(time.time())
+    t1 = time.time()
+    half = [r for r, s in zip(rates, stamps) if s >= t0 + 0.5 * (t1 - t0)]
+    return {"burst_tops": max(rates), "sustained_tops": float(np.median(half)), "launches": len(rates), "seconds": round(t1 - t0, 2),
+            "clocks": sampler.window(t0 + 0.5 * (t1 - t0), t1)}
 
 
 def run_ours(args):
@@ -172,14 +220,18 @@ def run_ours(args):
     sharding = importlib.import_module("3dreconstruction_b200.sharding")
     synth = pkg.synth
 
-    n_images = sharding.images_for_pairs_per_gpu(world, PAIRS_PER_GPU)
+    strong = args.scaling == "strong"
+    n_images = CONFIG3_IMAGES if strong else sharding.images_for_pairs_per_gpu(world, PAIRS_PER_GPU)
     descs = synth.collection(SYNTH_CONFIG, n_images, ROWS)
     # pinned host staging, so the e2e leg's H2D is a true async PCIe copy
     pinned = [torch.empty((ROWS, 128), dtype=torch.uint8).pin_memory() for _ in range(n_images)]
     for t, d in zip(pinned, descs):
         t.numpy()[:] = d
     descs = [t.numpy() for t in pinned]
-    feats = [synth.features(SYNTH_CONFIG, k, ROWS)[:, :2].copy() for k in range(n_images)]
+    pinned_f = [torch.empty((ROWS, 2), dtype=torch.float32).pin_memory() for _ in range(n_images)]
+    for k, t in enumerate(pinned_f):
+        t.numpy()[:] = synth.features(SYNTH_CONFIG, k, ROWS)[:, :2]
+    feats = [t.numpy() for t in pinned_f]
     rows = [ROWS] * n_images
     all_pairs = pkg.pairs_exhaustive(n_images)
     my_pairs, (b0, b1) = sharding.shard_pairs(all_pairs, rows, rank, world)
@@ -196,19 +248,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce(x, dist.ReduceOp.MAX) if world > 1 else x
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce(x, dist.ReduceOp.SUM) if world > 1 else x
 
     # ---------------- value: descriptors resident in HBM
     ctx.upload_images(descs, pinned=True)
@@ -231,62 +282,44 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     wall1 = time.time()
-    clocks = sampler.stop(wall0, wall1)
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.window(wall0, wall1)
+    step_ms_rank = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(step_ms_rank)
     total_pairs = sum_over_ranks(float(len(my_pairs)))
     value = total_pairs * args.steps / (ms * 1e-3)
     gpu_launches = int(sum_over_ranks(float(launches)))
 
-    # ---------------- e2e: host buffers -> public collection API -> matches on the host, every step
-    host_threads = max(1, (os.cpu_count() or 1) // world)   # the ranks of one box share its host cores
-    matcher = pkg.MatcherCudaAllInMemory(RATIO, ctx, host_threads=host_threads)
-    for _ in range(1):
-        matcher.LoadArrays(descs, feats)
-        matcher._ctx.match_collection(my_pairs, rs, host_threads, collect=False)
+    # ---------------- e2e: host buffers -> public collection API -> matches on the host, every step.  Every rank reads
+    # the collection over its own PCIe link (pinned staging, one asynchronous copy per image) -- no collective at all.
+    matcher = pkg.MatcherCudaAllInMemory(RATIO, ctx)
+    matcher.LoadArrays(descs, feats)
+    ctx.match_collection(my_pairs, rs, collect=False)
     barrier()
     t0 = time.time()
-    e2e_matches = 0
-    # N > 1: rank 0 alone reads the collection over PCIe; the replicas of the other GPUs arrive over NVLink (one NCCL
-    # broadcast of the arena), instead of N concurrent PCIe uploads of the same bytes
-    stage = torch.empty((n_images * ROWS, 128), dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
-    host_all = None
-    if world > 1 and rank == 0:
-        host_all = torch.empty((n_images * ROWS, 128), dtype=torch.uint8).pin_memory()
-        for k, d in enumerate(descs):
-            host_all[k * ROWS:(k + 1) * ROWS].numpy()[:] = d
-
-    def load_step():
-        if world == 1:
-            matcher.LoadArrays(descs, feats)                              # H2D of every descriptor array (+ norms kernel)
-            return
-        if rank == 0:
-            stage.copy_(host_all, non_blocking=True)                      # the one H2D of the job
-        dist.broadcast(stage, src=0)                                      # NVLink / NVSwitch
-        torch.cuda.current_stream().synchronize()
-        ctx.upload_images_device([stage.data_ptr() + k * ROWS * 128 for k in range(n_images)], rows)   # D2D into the arena
-        ctx.set_features(feats)
-
-    if world > 1:
-        load_step()
-        ctx.match_collection(my_pairs, rs, host_threads, collect=False)
-        barrier()
-        t0 = time.time()
+    e2e_matches, digest = 0, 0
     for _ in range(args.steps):
-        load_step()
-        pm = ctx.match_collection(my_pairs, rs, host_threads, collect=False)   # kernels + D2H + host de-dup (row 13)
+        matcher.LoadArrays(descs, feats)                                 # H2D of every descriptor array + coordinates (+ norms kernel)
+        pm = ctx.match_collection(my_pairs, rs, collect=False)           # kernels (rows 7-13) + D2H of the matches
         e2e_matches = int(pm.offsets[pm.n_pairs])
     barrier()
     e2e_s = max_over_ranks(time.time() - t0)
     e2e_value = total_pairs * args.steps / e2e_s
-    h2d = n_images * ROWS * 128 + len(my_pairs) * 24 + (len(my_pairs) + 1) * 4   # per step; at N > 1 only rank 0 reads the descriptors over PCIe
-    d2h = n_matches * 8 + len(my_pairs) * 4 + (len(my_pairs) + 1) * 8 + 8
+    digest, _ = _pair_digest(pm, my_pairs, len(my_pairs))                # after the timed region
+    h2d = n_images * ROWS * (128 + 8) + len(my_pairs) * 24 + (len(my_pairs) + 1) * 4
+    d2h = e2e_matches * 8 + len(my_pairs) * 4 + (len(my_pairs) + 1) * 8 + 16
+    # all-reduced checksum: (sum of per-pair hashes mod 2^64, total matches) -- split into 32-bit halves to stay exact in f64
+    dig_lo = int(sum_over_ranks(float(digest & 0xFFFFFFFF)))
+    dig_hi = int(sum_over_ranks(float(digest >> 32)))
+    digest_all = ((dig_hi << 32) + dig_lo) & 0xFFFFFFFFFFFFFFFF
+    matches_all = int(sum_over_ranks(float(e2e_matches)))
 
-    # ---------------- roofline of the dominant kernel (this rank)
+    # ---------------- roofline of the dominant kernel (this rank) against the int8 rate measured now
+    probe = probe_int8(ctx, sampler) if rank == 0 else None
+    sampler.stop()
     peaks, peak_src = _peaks()
     ops_per_pair = 2.0 * ROWS * ROWS * 128
-    achieved = ops_per_pair * len(my_pairs) * args.steps / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0
-    peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    probe_ops, _ = ctx.probe_i8_peak(20000)
+    ops_total = ops_per_pair * len(my_pairs) * args.steps
+    achieved = ops_total / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "knn2_traffic.json")
     if os.path.exists(tp):
@@ -294,15 +327,22 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {
-        "bound": "tensor", "kernel": "knn2_kernel (tcgen05 kind::i8 GEMM + fused top-2 epilogue)",
-        "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, 2 ops per MAC)", "frac": achieved / peak if peak else None,
-        "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peak_src}); kind::i8 issues at twice the bf16 rate",
-        "frac_of_nominal_4500": achieved / 4500.0, "probe_i8_tops_mma_only_burst": probe_ops / 1e12,
-        "frac_of_probe": achieved / (probe_ops / 1e12) if probe_ops else None,
-        "algorithmic_ops_per_launch": ops_per_pair * len(my_pairs), "launch_ms": knn_ms / max(knn_launches, 1),
-        "share_of_step": knn_ms / ev0.elapsed_time(ev1), "traffic": traffic,
-    }
+    roofline = None
+    if rank == 0:
+        peak = probe["sustained_tops"]
+        roofline = {
+            "bound": "tensor", "kernel": "knn2_kernel (tcgen05 cta_group::2 kind::i8 GEMM + fused top-2 epilogue; incl. the second pass over ambiguous queries)",
+            "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, 2 ops per MAC)", "frac": achieved / peak if peak else None,
+            "peak_source": "of measured int8: this run's MMA-only probe (mvgcuda_probe_i8_peak: back-to-back tcgen05.mma kind::i8 on every SM), "
+                           f"sustained for {probe['seconds']} s under the clock sampler; MEASURED_PEAKS.json ({peak_src}) holds no int8 figure",
+            "int8_probe": probe,
+            "frac_of_burst_probe": achieved / probe["burst_tops"] if probe["burst_tops"] else None,
+            "frac_of_nominal_4500": achieved / NOMINAL_INT8_TOPS,
+            "frac_of_2x_bf16_sustained_measured_peaks": achieved / (2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))),
+            "launches": knn_launches, "algorithmic_ops_per_launch": ops_total / max(knn_launches, 1),
+            "launch_ms": knn_ms / max(knn_launches, 1),
+            "share_of_step": knn_ms / step_ms_rank, "traffic": traffic,
+        }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -311,6 +351,9 @@ def run_ours(args):
         cpu = cpu_reference_run(nq=nq)
         cpu.pop("seconds", None)
         cpu.pop("pairs_equiv", None)
+        one = cpu_reference_run(nq=max(64, nq // 8), threads=1)                            # the reference's shipped configuration
+        cpu["single_thread"] = {"value": one["value"], "unit": "pairs/s", "cores": 1, "sample": one["sample"],
+                                "note": "the reference as shipped: USE_OPENMP is defined nowhere in its tree (matcher_all_in_memory.h:87-89)"}
         try:  # the reference's shipped default matcher (FLANN kd-tree, approximate + randomised): speed only
             fl = cpu_reference_run(nq=ROWS, flann=True)
             cpu["flann_kdtree"] = {"value": fl["value"], "unit": "pairs/s", "cores": fl["cores"], "sample": fl["sample"],
@@ -321,10 +364,10 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8 operands, exact int32 accumulate/compare; fp32 only in the ratio test", "data": "synthetic",
-            "config": {"workload": f"exhaustive pairs over {n_images} images x {ROWS} u8 SIFT-128 (BASELINE config 3 at 1 GPU: 100 images, "
-                                   f"4950 pairs); {int(total_pairs)} pairs total, {len(my_pairs)} on rank 0, ratio {RATIO}",
+            "config": {"workload": f"exhaustive pairs over {n_images} images x {ROWS} u8 SIFT-128 (BASELINE config 3: 100 images, "
+                                   f"4950 pairs{'' if strong or world == 1 else '; weak scaling grows the collection'}); {int(total_pairs)} pairs total, {len(my_pairs)} on rank 0, ratio {RATIO}",
                        "n_images": n_images, "rows_per_image": ROWS, "pairs_total": int(total_pairs), "ratio": RATIO,
                        "sharding": "replicated descriptor arena, contiguous cost-balanced split of the pair list, no collective",
                        "l2": "per step 0.13 GB of descriptors + 0.79 GB of per-query records stream through HBM, larger than the 126 MB L2; no explicit flush",
@@ -333,9 +376,11 @@ def run_ours(args):
                        "device": info["name"]},
             "clocks": clocks, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "includes": ("H2D of all descriptors from pinned host memory" + (" on rank 0 + NCCL broadcast of the arena over NVLink to the other ranks" if world > 1 else "")) + ", norm kernel, matching kernels, D2H of matches, "
-                                f"host coordinate de-dup (IndexedMatchDecorator) on {host_threads} host threads per rank, overlapped with the GPU batches",
+                    "includes": "per step and rank: H2D of all descriptors + feature coordinates from pinned host memory (one async copy per image), norm kernel, "
+                                "matching kernels incl. the coordinate de-dup (IndexedMatchDecorator) on the GPU, D2H of the matches (overlapped with the next batch)",
                     "matches": e2e_matches},
+            "checksum": {"matches_total": matches_all, "pairs_hash_sum64": f"{digest_all:016x}",
+                         "note": "sum over ALL pairs (all ranks) of a per-pair hash of (i, j, match list): independent of sharding and order"},
             "roofline": roofline,
         }
         if cpu is not None:
@@ -353,6 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

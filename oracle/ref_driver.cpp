@@ -25,6 +25,9 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "mvg/utils/progress.h"
 using namespace std;
@@ -61,6 +64,17 @@ int ref_has_openmp() {
   return 1;
 #else
   return 0;
+#endif
+}
+// Team size of the bench loops below.  (The environment is only read when libgomp loads; torchrun exports
+// OMP_NUM_THREADS=1 to its workers, which silently made the "all cores" baseline single-threaded in round 1.)
+int ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
 #endif
 }
 

@@ -41,6 +41,14 @@ int main(int argc, char** argv) {
     std::vector<int> out(n + 1);
     for (int i = 0; i < n; ++i) { nd[i].x = v[i].x1; nd[i].y = v[i].y1; }
     const int m = mvgcuda::rbtree_dedup(nd.data(), n, out.data());
+    {  // the 16-bit node form (what the shared-memory kernel runs) must agree with the 32-bit one
+      std::vector<mvgcuda::RbNode16> nd16(n + 1);
+      std::vector<unsigned short> out16(n + 1);
+      for (int i = 0; i < n; ++i) { nd16[i].x = v[i].x1; nd16[i].y = v[i].y1; }
+      const int m16 = mvgcuda::rbtree_dedup(nd16.data(), n, out16.data());
+      if (m16 != m) { printf("case %d: 16-bit nodes keep %d, 32-bit %d\n", c, m16, m); return 1; }
+      for (int i = 0; i < m; ++i) if (out16[i] != out[i]) { printf("case %d: 16-bit nodes differ at %d\n", c, i); return 1; }
+    }
     if (m != (int)s.size()) { printf("case %d: size %d != %zu\n", c, m, s.size()); return 1; }
     int q = 0;
     for (const Elem& e : s) {

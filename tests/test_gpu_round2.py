@@ -121,10 +121,12 @@ def test_second_pass_planned_on_device_and_bounded_fallback(ctx, pkg, l1, et, re
         ctx.set_tuning()
 
 
-def test_gpu_coordinate_dedup_equals_reference_std_set(ctx, pkg, l0):
+@pytest.mark.parametrize("rows,ratio", [(1500, 0.9), (7000, 1.0)])
+def test_gpu_coordinate_dedup_equals_reference_std_set(ctx, pkg, l0, rows, ratio):
     """Row 13 on the GPU: heavy duplicate x / duplicate (x, y) features, against IndexedMatchDecorator<float>::getDeduplicated
-    of the reference itself (its std::set with the non-strict-weak comparator)."""
-    descs = synth.collection(16, 4, 1500)
+    of the reference itself (its std::set with the non-strict-weak comparator).  The small case runs in the shared-memory
+    kernel (16-bit nodes), the large one has pairs with more than 2,047 matches, which take the global-memory kernel."""
+    descs = synth.collection(16, 4, rows)
     feats = []
     rng = np.random.default_rng(5)
     for k, d in enumerate(descs):
@@ -135,7 +137,7 @@ def test_gpu_coordinate_dedup_equals_reference_std_set(ctx, pkg, l0):
     ctx.upload_images(descs)
     ctx.set_features(feats)
     pairs = pkg.pairs_exhaustive(4)
-    rs = float(pkg.square_f32(0.9))
+    rs = float(pkg.square_f32(ratio))
     raw = ctx.match_pairs(pairs, rs)
     col = ctx.match_collection(pairs, rs)
     dropped = 0
@@ -144,6 +146,7 @@ def test_gpu_coordinate_dedup_equals_reference_std_set(ctx, pkg, l0):
         assert np.array_equal(col.pair(p), want), (i, j)
         dropped += len(raw.pair(p)) - len(want)
     assert dropped > 20, "the inputs must actually exercise the de-duplication"
+    assert (raw.counts.max() > 2047) == (rows > 2047), raw.counts
 
 
 def test_driver_sharded_over_two_contexts_is_byte_identical(pkg, et, tmp_path):
