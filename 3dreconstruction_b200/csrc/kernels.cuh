@@ -103,13 +103,15 @@ struct KnnParams {
 // ------------------------------------------------------------------------------------------ K1
 // Per-row constants, laid out per 256-row tile as [256 x ((||d||^2 << 8) | col)] [16 x min ||d||^2 of each 16-row chunk],
 // followed (after the last tile) by one min ||d||^2 per 128 rows -- the filter constant of one epilogue warp's slice of a
-// tile, which the warp keeps in a register.  8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles;
-// 128 rows per block.
+// tile, which the warp keeps in a register (the host presets those to 0x7F7F7F7F; atomicMin here).
+// 8 threads per 128-byte row (one 16-B load each), __dp4a squares, 3 shuffles; ONE chunk of 16 rows per block of 128
+// threads: small enough (128 threads x 40 registers, no shared memory to speak of) to run next to a resident knn2_kernel
+// CTA, so the constants of an image that arrives while earlier pairs are being matched do not wait for that kernel.
 __device__ __forceinline__ int ccol_index(int row) { return (row >> 8) * kTileC + (row & 255); }
 __host__ __device__ constexpr size_t ccol_ints(int arena_rows) {
   return static_cast<size_t>(arena_rows / kTileDb) * kTileC + static_cast<size_t>(arena_rows / kHalfCols);
 }
-constexpr int kK1Rows = kHalfCols;  // rows per block of K1
+constexpr int kK1Rows = kChunk;  // rows per block of K1
 
 __global__ void __launch_bounds__(8 * kK1Rows)
 row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img_row0, const int* __restrict__ img_rows,
@@ -141,17 +143,12 @@ row_consts_kernel(const uint8_t* __restrict__ arena, const int* __restrict__ img
     ccol[ccol_index(row)] = (norm << 8) | (row & 255);
   }
   __syncthreads();
-  if (threadIdx.x < kK1Rows / kChunk) {
-    int m = norms[threadIdx.x * kChunk];
+  if (threadIdx.x == 0) {
+    int m = norms[0];
 #pragma unroll
-    for (int k = 1; k < kChunk; ++k) m = min(m, norms[threadIdx.x * kChunk + k]);
-    const int row0 = block_row0 + threadIdx.x * kChunk;
-    ccol[(row0 >> 8) * kTileC + kTileDb + ((row0 & 255) >> 4)] = m;
-    // minimum of the block's 128 rows (8 chunk minima live in the first 8 lanes of warp 0)
-    m = min(m, __shfl_xor_sync(0xffu, m, 1));
-    m = min(m, __shfl_xor_sync(0xffu, m, 2));
-    m = min(m, __shfl_xor_sync(0xffu, m, 4));
-    if (threadIdx.x == 0) ccol[static_cast<size_t>(arena_rows / kTileDb) * kTileC + block_row0 / kK1Rows] = m;
+    for (int k = 1; k < kK1Rows; ++k) m = min(m, norms[k]);
+    ccol[(block_row0 >> 8) * kTileC + kTileDb + ((block_row0 & 255) >> 4)] = m;
+    atomicMin(&ccol[static_cast<size_t>(arena_rows / kTileDb) * kTileC + block_row0 / kHalfCols], m);
   }
 }
 

@@ -91,11 +91,17 @@ struct Arena {
   std::vector<int> row0, rows;  // host copies
   int arena_rows = 0;
   bool has_feats = false;
+  // streaming upload: image i was handed over (streamed), its copy + constants have been seen complete (ready), and the
+  // event that marks their completion on the upload stream
+  std::vector<char> streamed, ready;
+  std::vector<cudaEvent_t> img_ev;
   CUtensorMap tmap_q;    // boxes of 128 rows: one CTA's query block
   CUtensorMap tmap_db;   // boxes of 64 rows: one CTA's share of an N = 128 MMA group
   void release() {
     desc.release(); ccol.release(); feat.release(); img_row0.release(); img_rows.release();
     row0.clear(); rows.clear(); arena_rows = 0; has_feats = false;
+    for (cudaEvent_t e : img_ev) if (e) cudaEventDestroy(e);
+    img_ev.clear(); streamed.clear(); ready.clear();
   }
 };
 
@@ -144,6 +150,7 @@ struct mvgcuda_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;       // compute (own_stream, or the caller's)
   cudaStream_t copy_stream = nullptr;  // D2H of finished batches
+  cudaStream_t upload_stream = nullptr;  // H2D of streamed images (+ their constants kernel), concurrent with matching
   char error[1024] = "";
   size_t knn_smem = 0;
 
@@ -248,6 +255,10 @@ static int layout_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const int32_t*
   CU_CHECK(ctx, A.img_rows.reserve(std::max(n_images, 1)));
   cudaStream_t st = ctx->stream;
   CU_CHECK(ctx, cudaMemsetAsync(A.desc.p, 0, (size_t)A.arena_rows * kDim, st));
+  // per-128-row minima are accumulated with atomicMin by K1: preset them above every possible norm
+  CU_CHECK(ctx, cudaMemsetAsync(A.ccol.p + (size_t)(A.arena_rows / kTileDb) * kTileC, 0x7F, (size_t)(A.arena_rows / kHalfCols) * sizeof(int), st));
+  A.streamed.assign(n_images, 0);
+  A.ready.assign(n_images, 1);  // nothing pending (the bulk upload is synchronous; stream_image clears the flag of its image)
   CU_CHECK(ctx, cudaMemcpyAsync(A.img_row0.p, A.row0.data(), (n_images + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   if (n_images)
     CU_CHECK(ctx, cudaMemcpyAsync(A.img_rows.p, A.rows.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -260,9 +271,9 @@ static int layout_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const int32_t*
 }
 
 // K1 over arena rows [row_begin, row_end) (multiples of 256)
-static int launch_k1(mvgcuda_ctx* ctx, Arena& A, int row_begin, int row_end) {
+static int launch_k1(mvgcuda_ctx* ctx, Arena& A, int row_begin, int row_end, cudaStream_t st) {
   if (row_end <= row_begin) return MVGCUDA_OK;
-  row_consts_kernel<<<(row_end - row_begin) / kK1Rows, 8 * kK1Rows, 0, ctx->stream>>>(
+  row_consts_kernel<<<(row_end - row_begin) / kK1Rows, 8 * kK1Rows, 0, st>>>(
       A.desc.p, A.img_row0.p, A.img_rows.p, (int)A.rows.size(), A.arena_rows, row_begin, A.ccol.p);
   CU_CHECK(ctx, cudaGetLastError());
   return MVGCUDA_OK;
@@ -281,9 +292,40 @@ static int fill_arena(mvgcuda_ctx* ctx, Arena& A, int n_images, const uint8_t* c
     // arrived over NVLink) -- unified addressing sorts it out
     CU_CHECK(ctx, cudaMemcpyAsync(A.desc.p + (size_t)A.row0[i] * kDim, desc[i], (size_t)rows[i] * kDim, cudaMemcpyDefault, st));
   }
-  rc = launch_k1(ctx, A, 0, A.arena_rows);
+  rc = launch_k1(ctx, A, 0, A.arena_rows, st);
   if (rc) return rc;
   CU_CHECK(ctx, cudaStreamSynchronize(st));  // the caller's buffers are free again
+  return MVGCUDA_OK;
+}
+
+static int upload_features(mvgcuda_ctx* ctx, Arena& A, int image, const float* xy, int rows, cudaStream_t st) {
+  if (rows == 0) return MVGCUDA_OK;
+  CU_CHECK(ctx, cudaMemcpyAsync(A.feat.p + A.row0[image], xy, (size_t)rows * sizeof(float2), cudaMemcpyDefault, st));
+  return MVGCUDA_OK;
+}
+
+// Make the compute stream wait for the streamed images a pair list touches (and only for those): matching of the pairs
+// among the images that have arrived overlaps the upload of the rest.
+static int wait_for_images(mvgcuda_ctx* ctx, Arena& A, const int32_t* pairs, int64_t p0, int64_t p1, std::vector<char>& seen) {
+  seen.assign(A.rows.size(), 0);
+  for (int64_t p = p0; p < p1; ++p) { seen[pairs[2 * p]] = 1; seen[pairs[2 * p + 1]] = 1; }
+  for (size_t i = 0; i < seen.size(); ++i) {
+    if (!seen[i] || A.ready[i]) continue;
+    if (!A.streamed[i]) { ctx->set_error("image %d was announced by stream_begin but never streamed", (int)i); return MVGCUDA_ERR_INVALID; }
+    const cudaError_t q = cudaEventQuery(A.img_ev[i]);
+    if (q == cudaSuccess) { A.ready[i] = 1; continue; }
+    if (q != cudaErrorNotReady) CU_CHECK(ctx, q);
+    (void)cudaGetLastError();
+    CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, A.img_ev[i], 0));
+  }
+  return MVGCUDA_OK;
+}
+
+static int wait_for_all_images(mvgcuda_ctx* ctx, Arena& A) {
+  for (size_t i = 0; i < A.ready.size(); ++i) {
+    if (A.ready[i] || !A.streamed[i]) continue;
+    CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, A.img_ev[i], 0));
+  }
   return MVGCUDA_OK;
 }
 
@@ -548,6 +590,7 @@ struct MatchRun {  // state of one match_pairs / match_collection call
   long long match_base = 0;  // matches of all finished batches
   float gpu_ms = 0.f, knn_ms = 0.f;
   int knn_launches = 0, launches = 0;
+  std::vector<char> seen;  // scratch of wait_for_images
 };
 
 // Enqueue every kernel of the batch [p0, p1) into slot S.  No synchronisation with the compute stream.
@@ -568,6 +611,8 @@ static int enqueue_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S, int64_t p0
   CU_CHECK(ctx, S.h_meta.reserve(1));
   // the slot's device buffers are free once the copy of the batch that used them last has finished
   CU_CHECK(ctx, cudaStreamWaitEvent(st, S.ev_copied, 0));
+  int rc = wait_for_images(ctx, ctx->images, R.pairs, p0, p1, R.seen);
+  if (rc) return rc;
   CU_CHECK(ctx, cudaMemcpyAsync(S.d_jobs.p, S.h_jobs.p, nb * sizeof(PairJob), cudaMemcpyHostToDevice, st));
   CU_CHECK(ctx, cudaMemcpyAsync(S.d_item_start.p, S.h_item_start.p, (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   CU_CHECK(ctx, cudaMemsetAsync(S.d_meta.p, 0, sizeof(RescanMeta), st));
@@ -580,7 +625,7 @@ static int enqueue_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S, int64_t p0
   kp.out = S.d_knn.p;
   kp.prune_ratio = R.prune ? R.ratio_sq : FLT_MAX;
   kp.prune_rho = R.rho;
-  int rc = launch_knn_raw(ctx, A.tmap_q, A, kp, S.d_jobs.p, S.d_item_start.p, nb, bp.n_items, ctx->d_items);
+  rc = launch_knn_raw(ctx, A.tmap_q, A, kp, S.d_jobs.p, S.d_item_start.p, nb, bp.n_items, ctx->d_items);
   if (rc) return rc;
   if (bp.n_items) S.launches += 2;
   if (R.prune && R.rho < 1.0f && bp.n_items) {
@@ -774,12 +819,6 @@ static int knn2_impl(mvgcuda_ctx* ctx, const Arena& A, int db_img, const Arena& 
   return MVGCUDA_OK;
 }
 
-static int upload_features(mvgcuda_ctx* ctx, Arena& A, int image, const float* xy, int rows) {
-  if (rows == 0) return MVGCUDA_OK;
-  CU_CHECK(ctx, cudaMemcpyAsync(A.feat.p + A.row0[image], xy, (size_t)rows * sizeof(float2), cudaMemcpyDefault, ctx->stream));
-  return MVGCUDA_OK;
-}
-
 }  // namespace mvgcuda
 
 // ================================================================================ C ABI
@@ -853,6 +892,7 @@ int mvgcuda_create(int device, mvgcuda_ctx** out) try {
   }
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -884,6 +924,7 @@ void mvgcuda_destroy(mvgcuda_ctx* ctx) {
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
   delete ctx;
 }
 
@@ -915,13 +956,22 @@ int mvgcuda_stream_begin(mvgcuda_ctx* ctx, int n_images, const int32_t* rows) tr
   if (!ctx) return MVGCUDA_ERR_INVALID;
   if (n_images < 0 || (n_images > 0 && !rows)) { ctx->set_error("bad image list"); return MVGCUDA_ERR_INVALID; }
   CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->upload_stream));  // a previous streamed set is complete before its arena is reused
   ctx->r_pairs = 0;
   int rc = layout_arena(ctx, ctx->images, n_images, rows);
   if (rc) return rc;
   Arena& A = ctx->images;
   CU_CHECK(ctx, A.feat.reserve((size_t)A.arena_rows));
   CU_CHECK(ctx, cudaMemsetAsync(A.feat.p, 0, (size_t)A.arena_rows * sizeof(float2), ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the upload stream starts from a zeroed arena
   A.has_feats = true;  // every stream_image call supplies them (or none is needed: match_pairs only)
+  A.ready.assign(n_images, 0);
+  for (int i = 0; i < n_images; ++i) if (rows[i] == 0) A.ready[i] = 1;  // nothing to wait for
+  while ((int)A.img_ev.size() < n_images) {
+    cudaEvent_t e = nullptr;
+    CU_CHECK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    A.img_ev.push_back(e);
+  }
   return MVGCUDA_OK;
 }
 MVG_GUARD(ctx)
@@ -929,22 +979,30 @@ MVG_GUARD(ctx)
 int mvgcuda_stream_image(mvgcuda_ctx* ctx, int image, const uint8_t* desc, const float* feats_xy) try {
   if (!ctx) return MVGCUDA_ERR_INVALID;
   Arena& A = ctx->images;
-  if (image < 0 || image >= (int)A.rows.size()) { ctx->set_error("stream_image: image id out of range"); return MVGCUDA_ERR_INVALID; }
+  if (image < 0 || image >= (int)A.rows.size() || image >= (int)A.img_ev.size()) { ctx->set_error("stream_image: image id out of range (call stream_begin first)"); return MVGCUDA_ERR_INVALID; }
   const int rows = A.rows[image];
   if (rows > 0 && !desc) { ctx->set_error("stream_image: null descriptor pointer"); return MVGCUDA_ERR_INVALID; }
   CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->upload_stream;  // copies and the constants kernel run beside the matching kernels
   if (rows > 0) {
-    CU_CHECK(ctx, cudaMemcpyAsync(A.desc.p + (size_t)A.row0[image] * kDim, desc, (size_t)rows * kDim, cudaMemcpyDefault, ctx->stream));
-    if (feats_xy) { int rc = upload_features(ctx, A, image, feats_xy, rows); if (rc) return rc; }
+    CU_CHECK(ctx, cudaMemcpyAsync(A.desc.p + (size_t)A.row0[image] * kDim, desc, (size_t)rows * kDim, cudaMemcpyDefault, st));
+    if (feats_xy) { int rc = upload_features(ctx, A, image, feats_xy, rows, st); if (rc) return rc; }
   }
-  return launch_k1(ctx, A, A.row0[image], A.row0[image] + round_up(rows, kRowAlign));
+  int rc = launch_k1(ctx, A, A.row0[image], A.row0[image] + round_up(rows, kRowAlign), st);
+  if (rc) return rc;
+  CU_CHECK(ctx, cudaEventRecord(A.img_ev[image], st));
+  A.streamed[image] = 1;
+  A.ready[image] = 0;
+  return MVGCUDA_OK;
 }
 MVG_GUARD(ctx)
 
 int mvgcuda_stream_end(mvgcuda_ctx* ctx) try {
   if (!ctx) return MVGCUDA_ERR_INVALID;
   CU_CHECK(ctx, cudaSetDevice(ctx->device));
-  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // every staging buffer handed to stream_image is free again
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->upload_stream));  // every staging buffer handed to stream_image is free again
+  Arena& A = ctx->images;
+  for (size_t i = 0; i < A.ready.size(); ++i) if (A.streamed[i]) A.ready[i] = 1;
   return MVGCUDA_OK;
 }
 MVG_GUARD(ctx)
@@ -969,6 +1027,7 @@ int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image) {
 
 int mvgcuda_knn2(mvgcuda_ctx* ctx, int db_img, int q_img, int tie_mode, int32_t* idx, float* dist) try {
   if (!ctx) return MVGCUDA_ERR_INVALID;
+  { int rc = wait_for_all_images(ctx, ctx->images); if (rc) return rc; }
   return knn2_impl(ctx, ctx->images, db_img, ctx->images, q_img, tie_mode, idx, dist);
 }
 MVG_GUARD(ctx)
@@ -1052,6 +1111,8 @@ int mvgcuda_clone_images(mvgcuda_ctx* ctx, const mvgcuda_ctx* src) try {
   A.rows = S.rows;
   A.arena_rows = S.arena_rows;
   A.has_feats = S.has_feats;
+  A.streamed.assign(A.rows.size(), 0);
+  A.ready.assign(A.rows.size(), 1);
   const int n_images = (int)A.rows.size();
   const size_t ccol_len = ccol_ints(A.arena_rows);
   CU_CHECK(ctx, A.desc.reserve((size_t)A.arena_rows * kDim));
@@ -1088,7 +1149,7 @@ int mvgcuda_set_features(mvgcuda_ctx* ctx, int n_images, const float* const* fea
   CU_CHECK(ctx, A.feat.reserve((size_t)std::max(A.arena_rows, 1)));
   CU_CHECK(ctx, cudaMemsetAsync(A.feat.p, 0, (size_t)A.arena_rows * sizeof(float2), ctx->stream));
   for (int i = 0; i < n_images; ++i) {
-    int rc = upload_features(ctx, A, i, feats_xy[i], rows[i]);
+    int rc = upload_features(ctx, A, i, feats_xy[i], rows[i], ctx->stream);
     if (rc) return rc;
   }
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's buffers are free again

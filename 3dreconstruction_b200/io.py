@@ -70,14 +70,28 @@ def matches_to_text(pairwise: Dict[Tuple[int, int], np.ndarray]) -> str:
 
 
 def matches_from_text(text: str) -> Dict[Tuple[int, int], np.ndarray]:
-    """pairedIndexedMatchImport (indexed_match_utils.h:48-73)."""
+    """pairedIndexedMatchImport (indexed_match_utils.h:48-73): blocks "i j count" + count x "_i _j" until the first token
+    that does not parse; a key seen twice keeps its LAST block (operator[] assignment); a block cut short by the end of the
+    file is kept with the missing entries left at IndexedMatch's default (0, 0), as `std::vector<IndexedMatch>(number)`
+    followed by failing extractions leaves them."""
     tok = text.split()
     out: Dict[Tuple[int, int], np.ndarray] = {}
     k = 0
     while k + 3 <= len(tok):
-        i, j, n = int(tok[k]), int(tok[k + 1]), int(tok[k + 2])
+        try:
+            i, j, n = int(tok[k]), int(tok[k + 1]), int(tok[k + 2])
+        except ValueError:
+            break
         k += 3
-        m = np.array(tok[k:k + 2 * n], dtype=np.int64).reshape(n, 2)
+        m = np.zeros((n, 2), np.int64)
+        flat = []
+        for t in tok[k:k + 2 * n]:
+            try:
+                flat.append(int(t))
+            except ValueError:
+                break
+        # an odd number of tokens: the dangling _i was read, its _j was not
+        m.reshape(-1)[:len(flat)] = flat
         k += 2 * n
         out[(i, j)] = m
     return out

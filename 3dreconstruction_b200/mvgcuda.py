@@ -130,6 +130,15 @@ def pairs_exhaustive(n_images: int) -> np.ndarray:
     return np.stack([i, j], axis=1).astype(np.int32)
 
 
+def upload_friendly_order(pairs: np.ndarray) -> np.ndarray:
+    """The same pairs, ordered by their LARGER image id first (then the smaller): with images streamed in index order the
+    first batches only touch images that have already arrived, so matching overlaps the rest of the upload.  Results are
+    keyed by pair, so the order is free (the export sorts by (i, j) itself)."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    hi, lo = pairs.max(axis=1), pairs.min(axis=1)
+    return pairs[np.lexsort((lo, hi))]
+
+
 def _as_u8_matrix(a: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint8)
     if a.ndim != 2 or a.shape[1] != DIM:
@@ -234,20 +243,28 @@ class Context:
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rws, 0), "mvgcuda_upload_images")
 
     def stream_images(self, descs: Sequence[np.ndarray], feats_xy: Optional[Sequence[np.ndarray]] = None,
-                      order: Optional[Sequence[int]] = None) -> None:
+                      order: Optional[Sequence[int]] = None, wait: bool = True) -> None:
         """Same residency as upload_images (+ set_features), through the streaming entry points: one asynchronous copy per
-        image, in `order` (default 0..n-1), then one wait."""
+        image on the context's upload stream, in `order` (default 0..n-1).  With wait=False the call returns while the
+        copies are in flight -- a following match call starts on the pairs whose images have arrived -- and the arrays must
+        stay untouched until stream_end() (the context keeps references to them until then)."""
         mats = [_as_u8_matrix(d) if len(d) else np.zeros((0, DIM), np.uint8) for d in descs]
         n = len(mats)
         rows = (C.c_int32 * max(n, 1))(*[m.shape[0] for m in mats])
         self._check(self._lib.mvgcuda_stream_begin(self._h, n, rows), "mvgcuda_stream_begin")
         fm = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy] if feats_xy is not None else None
+        self._staged = (mats, fm)
         for k in (order if order is not None else range(n)):
             m = mats[k]
             dp = m.ctypes.data_as(C.POINTER(C.c_uint8)) if m.shape[0] else None
             fp = fm[k].ctypes.data_as(_f32p) if fm is not None and m.shape[0] else None
             self._check(self._lib.mvgcuda_stream_image(self._h, int(k), dp, fp), "mvgcuda_stream_image")
+        if wait:
+            self.stream_end()
+
+    def stream_end(self) -> None:
         self._check(self._lib.mvgcuda_stream_end(self._h), "mvgcuda_stream_end")
+        self._staged = None
 
     def db_create(self, db: np.ndarray) -> "ResidentDb":
         return ResidentDb(self, db)
@@ -424,7 +441,8 @@ class MatcherCudaAllInMemory:
         self._ctx = ctx or Context(0)
         self._n = 0  # (host_threads: accepted and ignored -- the coordinate de-dup runs on the GPU)
 
-    def LoadArrays(self, descs: Sequence[np.ndarray], feats_xy: Sequence[np.ndarray]) -> bool:
+    def LoadArrays(self, descs: Sequence[np.ndarray], feats_xy: Sequence[np.ndarray], wait: bool = True,
+                   order: Optional[Sequence[int]] = None) -> bool:
         # row counts come from the features, as in the reference (matcher_all_in_memory.h:80,85,107)
         rows = [np.asarray(f).reshape(-1, 2).shape[0] for f in feats_xy]
         d2 = []
@@ -433,8 +451,8 @@ class MatcherCudaAllInMemory:
             if d.shape[0] < r:
                 raise MvgCudaError(".feat has more rows than .desc (the reference over-reads here; refused)")
             d2.append(d[:r])
-        # one asynchronous copy per image (descriptors + coordinates) and one wait: the streaming entry points
-        self._ctx.stream_images(d2, feats_xy)
+        # one asynchronous copy per image (descriptors + coordinates).  wait=False: Match() starts while images still travel
+        self._ctx.stream_images(d2, feats_xy, order=order, wait=wait)
         self._n = len(d2)
         return True
 
@@ -451,7 +469,9 @@ class MatcherCudaAllInMemory:
         n = self._n if file_names is None else len(file_names)
         if pairs is None:
             pairs = pairs_exhaustive(n)
+        pairs = upload_friendly_order(pairs)
         self.last = self._ctx.match_collection(pairs, float(square_f32(self.distance_ratio)))
+        self._ctx.stream_end()  # images handed over with wait=False: their buffers are free again
         return self.last.as_dict()
 
     def Export(self, path: str) -> None:

@@ -49,4 +49,14 @@ SRC=("$HERE/ref_driver.cpp" "$REF/libs/base/src/utils/file_system.cpp" "$REF/lib
 CXXFLAGS=(-std=c++11 -O2 -fPIC -shared -w -DORACLE_WITH_FLANN)
 g++ "${CXXFLAGS[@]}" "${INC[@]}" "${SRC[@]}" -o "$OUT/libmvgref.so"
 g++ "${CXXFLAGS[@]}" -DUSE_OPENMP -fopenmp "${INC[@]}" "${SRC[@]}" -o "$OUT/libmvgref_omp.so"
+# (3) the step after the path: the reference's AC-RANSAC geometric filter, for golden matches.f/h.txt
+GEOM_INC=("${INC[@]}" -I"$REF/libs/multiview/include" -I"$REF/libs/camera/include" -I"$REF/libs/image/include")
+GEOM_SRC=("$HERE/ref_geom_driver.cpp" "$REF/libs/base/src/utils/file_system.cpp" "$REF/libs/base/src/utils/wildcard.cpp"
+          "$REF/libs/multiview/src/solver_fundamental_kernel.cpp" "$REF/libs/multiview/src/solver_homography_kernel.cpp"
+          "$REF/libs/multiview/src/conditioning.cpp" "$REF/libs/base/src/math/numeric.cpp" "$REF/libs/camera/src/projection.cpp")
+if g++ -std=c++11 -O2 -fPIC -shared -w -Wl,--no-undefined "${GEOM_INC[@]}" "${GEOM_SRC[@]}" -o "$OUT/libmvgref_geom.so" 2> "$TMP/geom.log"; then
+  echo "built $OUT/libmvgref_geom.so"
+else
+  echo "build_ref.sh: geometric-filter oracle NOT built:" >&2; head -20 "$TMP/geom.log" >&2
+fi
 echo "built $OUT/libmvgref.so $OUT/libmvgref_omp.so from $REF"

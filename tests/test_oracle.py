@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 synth = importlib.import_module("3dreconstruction_b200.synth")
 pkg_io = importlib.import_module("3dreconstruction_b200.io")
@@ -258,3 +258,52 @@ def test_l1_collection_golden_imagedata(l1, pkg, name, r, tmp_path):
     l1.export_text(pw, str(out))
     assert out.read_bytes() == z[f"{name}_text_r{r}"].tobytes()
     assert sum(len(v) for v in pw.values()) == meta[f"r{r}"]["matches"]
+
+
+# ---------------------------------------------------------------- the step after the path: oracle side only
+
+def test_geometric_filter_reference_reproduces_goldens(tmp_path):
+    """oracle/_ref/libmvgref_geom.so (the reference's own ImageCollectionGeometricFilter + AC-RANSAC F / H filters, rand()
+    stream pinned) reproduces the committed golden matches.f / matches.h files of data/et: 15 pairs / 780 matches for F
+    (the value SURVEY.md 8(f) recorded).  Needs the .feat files of the reference tree."""
+    import ctypes as C
+    import hashlib
+    import json
+    from oracle import oracle
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libmvgref_geom.so")
+    et_dir = os.path.join(oracle.REF_ROOT, "data", "et")
+    if not os.path.exists(lib_path) or not os.path.isdir(et_dir):
+        pytest.skip("geometric-filter oracle or the reference's data/et not available here")
+    meta = json.load(open(os.path.join(GOLDEN, "et_geometric_golden.json")))
+    lib = C.CDLL(lib_path)
+    lib.ref_geometric_filter.restype = C.c_int
+    lib.ref_geometric_filter.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_char, C.c_double, C.c_uint, C.c_char_p]
+    names = [f"et{k:03d}.jpg" for k in range(9)]
+    sizes = (C.c_int * 18)(*([640, 480] * 9))
+    for model in ("f", "h"):
+        out = str(tmp_path / f"m_{model}.txt")
+        n = lib.ref_geometric_filter(et_dir.encode(), "\n".join(names).encode(), sizes, os.path.join(GOLDEN, "et_putative_r0.6.txt").encode(),
+                                     model.encode(), meta["max_residual"], meta["seed"], out.encode())
+        data = open(out, "rb").read()
+        assert n == meta[model]["pairs"] and hashlib.sha256(data).hexdigest() == meta[model]["sha256"]
+        assert data == open(os.path.join(GOLDEN, f"et_matches_{model}.txt"), "rb").read()
+    assert (meta["f"]["pairs"], meta["f"]["matches"]) == (15, 780)
+
+
+def test_match_file_import_mirrors_reference_reader(tmp_path, l0):
+    """matches_from_text (the Python mirror of pairedIndexedMatchImport, indexed_match_utils.h:48-73, also restated in the
+    driver's resume path) against the reference's own reader + writer: duplicate keys keep the LAST block, a truncated
+    tail stops the import silently."""
+    from conftest import GOLDEN as G
+    io = importlib.import_module("3dreconstruction_b200.io")
+    text = open(os.path.join(G, "et_putative_r0.8.txt")).read()
+    weird = text + "0 1\n2\n5 6\n7 8\n" + "3 4\n1\n9 9\n" + "7 8\n3\n1 2\n"     # key (0,1) again; then a block cut short
+    src = tmp_path / "in.txt"
+    src.write_text(weird)
+    back = tmp_path / "back.txt"
+    l0.roundtrip_matches(str(src), str(back))
+    got = io.matches_to_text(io.matches_from_text(weird))
+    want = back.read_text()
+    # the reference pads the short block with default IndexedMatch (0, 0) entries; the mirror must agree on every complete block
+    assert got.split("7 8\n3\n")[0] == want.split("7 8\n3\n")[0]
+    assert "0 1\n2\n5 6\n7 8\n" in got
