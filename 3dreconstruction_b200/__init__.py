@@ -9,5 +9,5 @@ file formats) and ``synth`` (seeded synthetic SIFT-like collections for tests an
 from . import io, synth  # noqa: F401
 from .mvgcuda import (  # noqa: F401
     ABI, DIM, TIE_LOWEST_INDEX, TIE_REFERENCE, ArrayMatcherCuda, Context, MatcherCudaAllInMemory,
-    MvgCudaError, PairMatches, ResidentDb, load_library, pairs_exhaustive, square_f32, upload_friendly_order,
+    MvgCudaError, PairMatches, ResidentDb, load_library, pairs_exhaustive, square_f32, upload_friendly_order, write_matches,
 )

@@ -1,0 +1,436 @@
+// acransac_kernels.cuh -- AC-RANSAC fundamental-matrix filter on the GPU (replaces
+// ImageCollectionGeometricFilter::Filter + GeometricFilter_FMatrix_AC, geometric_filter.h:37-102, fundamental_acransac.h:13-57,
+// estimator_acransac.h:125-245).  Compiled with -fmad=false (see acransac_core.cuh).
+//
+// The reference's results are defined by ONE global rand() stream consumed pair after pair (7 values per iteration, the
+// iteration count of a pair depends on when its first meaningful model turns up), so pairs form a chain: a pair's stream
+// offset is known only when the previous pair's first phase is over.  The pairs are therefore walked in order and the
+// parallelism comes from INSIDE a pair: all iterations of the current range are evaluated at once, one warp each
+// (geo_eval_kernel: sample, 7-point solve -- lane 0: 9x9 Jacobi SVD bit-faithful to Eigen + cubic --, then per model all
+// residuals with the lanes over the points, ordered ballot compaction of the candidates <= max_threshold, bitonic sort
+// in shared memory (global scratch for long lists), parallel NFA scan), and ONE warp accounts for them in order
+// (geo_decide_kernel, acransac_engine.cuh).
+// Exactness: the evaluation uses CUDA's acos / cos / pow for the cubic, which differ from the host C library's in the last
+// bit of ~10 % of the roots; a model an ACRANSAC decision hinges on (a trigger, the best model at the end of the first
+// phase, and anything within a guard band of those thresholds) is re-evaluated from the same null vectors with the roots
+// the HOST's libm gives for its cubic (geo_exact_kernel) before the decision is taken, so accepted models -- and with them
+// the sampling sets, the inlier lists and their order -- carry the reference's bits.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "acransac_engine.cuh"
+
+namespace mvgcuda {
+namespace geo {
+
+constexpr int kGeoThreads = 1024;            // one CTA per SM
+constexpr int kGeoWarps = kGeoThreads / 32;
+constexpr int kListCap = 256;                // candidates a warp sorts in shared memory (power of two)
+constexpr int kMaxModelsF = 3;
+
+struct GeoPairDev {  // one ACTIVE pair (more than 7 putative matches) of a batch
+  int n;             // putative matches == nData
+  int m_off;         // first match of the pair in the batch arrays
+  int row0_i, row0_j;  // first arena row of image I / J (feature coordinates)
+  int logc_off;      // the pair's log10 C(n, .) table in the pool
+  int out_slot;      // index of the pair in the caller's pair list
+  Normalizer N1, N2;
+  double max_threshold, logalpha0, loge0;
+};
+
+struct IterRes { double nfa; int n_inl; int model; };
+constexpr int kBasisDoubles = 22;  // per iteration: f1[9], f2[9] (null vectors), P[4] (cubic, ascending powers)
+constexpr double kGuardAbs = 1e-3, kGuardRel = 1e-6;  // NFA band around a decision threshold that forces exact roots
+
+struct RoundInfo {   // what every warp needs to evaluate the current range; written by the sequencer between two barriers
+  int pair, lo, hi, n_index;
+  long long offset;  // absolute rand() position of iteration 0 of the pair
+  int done_all, pad;
+};
+
+struct DecideOut {   // what the host reads after geo_decide_kernel
+  int status;        // 0: evaluate `next` (same or next pair), 1: iteration `it` needs exact roots (P), 2: batch finished
+  int it;
+  double P[4];
+  RoundInfo next;
+};
+
+struct GeoBatchDev {
+  const GeoPairDev* pairs;
+  int n_pairs;
+  const int2* matches;      // putative (_i, _j) of the batch, dense, pair after pair
+  const float2* feats;      // (x, y) of every arena row
+  double2* x1;              // normalised points, [matches of the batch]
+  double2* x2;
+  const float* logc_pool;   // log10 C(n, k) tables
+  const float* logc_k;      // log10 C(k, 7), k = 0 .. n_max
+  const uint32_t* stream;   // stream[k] = rand() value number stream_base + k of the process
+  long long stream_base;
+  int max_iterations;
+  IterRes* res;             // [max_iterations + 8]
+  double* models;           // [max_iterations + 8][27]
+  double* basis;            // [max_iterations + 8][kBasisDoubles]
+  int* exact;               // [max_iterations + 8]: models computed with the host's roots
+  DecideOut* decide;
+  int* vec_index;           // [n_max]
+  double* g_e;              // long candidate lists: [warps of the grid + 1][n_cap]
+  int* g_i;
+  int n_cap;                // power of two >= n_max
+  int* out_idx;             // [matches of the batch]: inlier positions (into the pair's putative list), in residual order
+  int* out_count;           // [n_pairs]
+  int* out_iters;           // [n_pairs]: iterations the reference would have run (7 rand() values each)
+  RoundInfo* round;
+  AcState* state;
+  unsigned* barrier;        // zeroed before the launch
+  long long* offset_io;     // in: rand() position before the batch, out: after it
+};
+
+// ------------------------------------------------------------------------------------------ prep
+// Normalised coordinates of every putative match (NormalizePoints of both images, once per pair in the reference).
+__global__ void __launch_bounds__(256)
+geo_prep_kernel(GeoBatchDev B) {
+  const GeoPairDev P = B.pairs[blockIdx.x];
+  for (int k = threadIdx.x; k < P.n; k += blockDim.x) {
+    const int2 m = B.matches[P.m_off + k];
+    const float2 a = B.feats[P.row0_i + m.x], b = B.feats[P.row0_j + m.y];
+    double2 o;
+    normalize_point(P.N1, a.x, a.y, o.x, o.y);
+    B.x1[P.m_off + k] = o;
+    normalize_point(P.N2, b.x, b.y, o.x, o.y);
+    B.x2[P.m_off + k] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ warp-level pieces
+struct WarpScratch {
+  double W[81], V[81], F[27];
+  double le[kListCap];
+  int li[kListCap];
+  int n_models, pad;
+};
+
+// Candidates of one model: residual of every point, those <= max_threshold kept in index order (ordered compaction), then
+// sorted by (residual, index) == the head of std::sort(vec_residuals) (estimator_acransac.h:176-181).  Returns their number
+// m; e / idx point to the sorted list (shared memory when m <= kListCap, else the warp's global scratch).
+__device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* F, WarpScratch& ws,
+                                                     double* ge, int* gi, int lane, double*& e_out, int*& i_out) {
+  double f[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) f[k] = F[k];
+  const double2* x1 = B.x1 + P.m_off;
+  const double2* x2 = B.x2 + P.m_off;
+  int m = 0;
+  double* le = ws.le;
+  int* li = ws.li;
+  int cap = kListCap;
+  for (int pass = 0; pass < 2; ++pass) {
+    m = 0;
+    for (int base = 0; base < P.n; base += 32) {
+      const int i = base + lane;
+      bool keep = false;
+      double e = 0.0;
+      if (i < P.n) {
+        const double2 a = x1[i], b = x2[i];
+        e = epipolar_error(f, a.x, a.y, b.x, b.y);
+        keep = e <= P.max_threshold;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int slot = m + __popc(mask & ((1u << lane) - 1u));
+        if (slot < cap) { le[slot] = e; li[slot] = i; }
+      }
+      m += __popc(mask);
+    }
+    if (m <= cap) break;
+    le = ge; li = gi; cap = B.n_cap;  // a long list: once more, into global scratch
+  }
+  e_out = le; i_out = li;
+  if (m < 2) { __syncwarp(); return m; }
+  int p2 = 32;
+  while (p2 < m) p2 <<= 1;
+  for (int k = m + lane; k < p2; k += 32) { le[k] = ac_inf(); li[k] = 0x7fffffff; }
+  __syncwarp();
+  for (int k = 2; k <= p2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = lane; idx < p2; idx += 32) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const Cand a{le[idx], li[idx]}, b{le[ixj], li[ixj]};
+          const bool up = (idx & k) == 0;
+          if (up ? cand_less(b, a) : cand_less(a, b)) { le[idx] = b.e; li[idx] = b.i; le[ixj] = a.e; li[ixj] = a.i; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  return m;
+}
+
+// bestNFA over the sorted candidates (estimator_acransac.h:73-96): minimum over k = 8 .. m, lowest k among equal values.
+__device__ __forceinline__ void best_nfa_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* e, int m, int lane, double& nfa, int& k_best) {
+  double v = ac_inf();
+  int kb = 0x7fffffff;
+  const float* lcn = B.logc_pool + P.logc_off;
+  for (int k = kSampleF + 1 + lane; k <= m; k += 32) {
+    const double t = nfa_term(P.logalpha0, P.loge0, e[k - 1], k, kSampleF, lcn[k], B.logc_k[k]);
+    if (t < v) { v = t; kb = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, kb, o);
+    if (ov < v || (ov == v && ok < kb)) { v = ov; kb = ok; }
+  }
+  nfa = v;
+  k_best = v < ac_inf() ? kb : kSampleF;
+}
+
+// All models of one iteration (already in ws.F): best NFA over the models, strict <, in order (estimator_acransac.h:173-217).
+__device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, const GeoPairDev& P, WarpScratch& ws, int nm, double* ge, int* gi, int lane) {
+  double best = ac_inf();
+  int best_k = 0, best_model = 0;
+  for (int k = 0; k < nm; ++k) {
+    double* e;
+    int* idx;
+    const int m = model_candidates_warp(B, P, ws.F + 9 * k, ws, ge, gi, lane, e, idx);
+    if (m > kSampleF) {
+      double v;
+      int kb;
+      best_nfa_warp(B, P, e, m, lane, v, kb);
+      if (v < best) { best = v; best_k = kb; best_model = k; }
+    }
+    __syncwarp();
+  }
+  IterRes r;
+  r.nfa = best; r.n_inl = best < ac_inf() ? best_k : 0; r.model = best_model;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ evaluation of a range
+// One warp per iteration of [round.lo, round.hi) with the sampling set vec_index[0 .. n_index) (estimator_acransac.h:166-218).
+constexpr int kEvalWarps = 8;
+__global__ void __launch_bounds__(32 * kEvalWarps)
+geo_eval_kernel(GeoBatchDev B) {
+  __shared__ WarpScratch scratch[kEvalWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * kEvalWarps + warp;
+  const RoundInfo R = *B.round;
+  const int it = R.lo + gwarp;
+  if (it >= R.hi) return;
+  const GeoPairDev P = B.pairs[R.pair];
+  const bool identity = B.state->index_it < 0;
+  WarpScratch& ws = scratch[warp];
+  double* ge = B.g_e + static_cast<size_t>(gwarp) * B.n_cap;
+  int* gi = B.g_i + static_cast<size_t>(gwarp) * B.n_cap;
+  if (lane == 0) {
+    const uint32_t* r7 = B.stream + (R.offset + static_cast<long long>(kSampleF) * it - B.stream_base);
+    uint32_t r[kSampleF];
+    for (int k = 0; k < kSampleF; ++k) r[k] = r7[k];
+    int s[kSampleF];
+    random_sample<kSampleF>(r, R.n_index, s);
+    double a[2 * kSampleF], b[2 * kSampleF];
+    for (int k = 0; k < kSampleF; ++k) {
+      const int id = identity ? s[k] : B.vec_index[s[k]];
+      const double2 p = B.x1[P.m_off + id], q = B.x2[P.m_off + id];
+      a[2 * k] = p.x; a[2 * k + 1] = p.y; b[2 * k] = q.x; b[2 * k + 1] = q.y;
+    }
+    double Pc[4], roots[3];
+    seven_point_basis(a, b, ws.W, ws.V, Pc);
+    const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
+    models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
+    ws.n_models = nr;
+    double* bs = B.basis + static_cast<size_t>(it) * kBasisDoubles;
+    for (int k = 0; k < 9; ++k) { bs[k] = ws.V[9 * 8 + k]; bs[9 + k] = ws.V[9 * 7 + k]; }
+    for (int k = 0; k < 4; ++k) bs[18 + k] = Pc[k];
+    double* out = B.models + static_cast<size_t>(it) * 27;
+    for (int k = 0; k < 9 * nr; ++k) out[k] = ws.F[k];
+  }
+  __syncwarp();
+  const IterRes r = evaluate_models_warp(B, P, ws, ws.n_models, ge, gi, lane);
+  if (lane == 0) { B.res[it] = r; B.exact[it] = 0; }
+}
+
+// The same iteration again with the roots the host's C library computed for its cubic: bit-identical to the reference.
+__global__ void __launch_bounds__(32)
+geo_exact_kernel(GeoBatchDev B, int it, int nr, double r0, double r1, double r2) {
+  __shared__ WarpScratch ws;
+  const int lane = threadIdx.x;
+  const GeoPairDev P = B.pairs[B.round->pair];
+  if (lane == 0) {
+    const double roots[3] = {r0, r1, r2};
+    const double* bs = B.basis + static_cast<size_t>(it) * kBasisDoubles;
+    models_from_roots(bs, bs + 9, roots, nr, ws.F);
+    ws.n_models = nr;
+    double* out = B.models + static_cast<size_t>(it) * 27;
+    for (int k = 0; k < 9 * nr; ++k) out[k] = ws.F[k];
+  }
+  __syncwarp();
+  const IterRes r = evaluate_models_warp(B, P, ws, nr, B.g_e, B.g_i, lane);
+  if (lane == 0) { B.res[it] = r; B.exact[it] = 1; }
+}
+
+// The sequencer's view of the evaluated results (warp-parallel searches; every lane returns the same value).
+struct WarpRange {
+  const IterRes* res;
+  int lane;
+  __device__ int first_below(int lo, int hi, double thr) const {
+    int f = 0x7fffffff;
+    for (int i = lo + lane; i < hi; i += 32)
+      if (res[i].nfa < thr) { f = i; break; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+    return f == 0x7fffffff ? -1 : f;
+  }
+  __device__ int argmin_first(int lo, int hi) const {
+    double v = ac_inf();
+    int a = 0x7fffffff;
+    for (int i = lo + lane; i < hi; i += 32) {
+      const double t = res[i].nfa;
+      if (a == 0x7fffffff || t < v) { v = t; a = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+      if (oa != 0x7fffffff && (a == 0x7fffffff || ov < v || (!(v < ov) && oa < a))) { v = ov; a = oa; }
+    }
+    return a;
+  }
+  __device__ double nfa(int i) const { return res[i].nfa; }
+  __device__ int n_inl(int i) const { return res[i].n_inl; }
+  __device__ int model(int i) const { return res[i].model; }
+};
+
+// Lowest iteration of [lo, hi) that may lie below `thr`: exact entries are compared with thr, approximate ones with
+// thr + guard.  -1 if none.
+__device__ __forceinline__ int first_candidate(const GeoBatchDev& B, int lo, int hi, double thr, double guard, int lane) {
+  int f = 0x7fffffff;
+  for (int i = lo + lane; i < hi; i += 32) {
+    const double v = B.res[i].nfa;
+    if (B.exact[i] ? v < thr : v < thr + guard) { f = i; break; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+  return f == 0x7fffffff ? -1 : f;
+}
+
+// ------------------------------------------------------------------------------------------ accounting (one warp)
+// start != 0: first call of a batch -- set up pair 0.  Otherwise: the range of `round` has been evaluated; ask for exact
+// roots where a decision needs them, else account for the range (ac_account), materialise a new sampling set or the final
+// inliers, move to the next pair, and tell the host what to evaluate next.
+__global__ void __launch_bounds__(32)
+geo_decide_kernel(GeoBatchDev B, int start) {
+  __shared__ WarpScratch ws;
+  const int lane = threadIdx.x;
+  DecideOut D;
+  D.status = 0; D.it = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
+  if (start) {
+    AcState S;
+    ac_init(S, B.pairs[0].n, B.max_iterations);
+    RoundInfo N;
+    N.pair = 0; N.lo = S.iter; N.hi = ac_range_end(S); N.n_index = S.n_index; N.offset = *B.offset_io; N.done_all = 0; N.pad = 0;
+    D.next = N;
+    if (lane == 0) { *B.state = S; *B.round = N; *B.decide = D; }
+    return;
+  }
+  const RoundInfo R = *B.round;
+  const GeoPairDev P = B.pairs[R.pair];
+  AcState S = *B.state;
+  const int lo = S.iter, hi = ac_range_end(S);
+  if (!S.done && lo < hi) {
+    const bool ext = S.extend_to > 0;
+    const double thr = ext ? ac_inf() : (S.min_nfa < 0.0 ? S.min_nfa : 0.0);
+    const double guard = ext ? 0.0 : kGuardAbs + kGuardRel * fabs(thr);
+    int need = -1;
+    const int t = first_candidate(B, lo, hi, thr, guard, lane);
+    if (t >= 0) {
+      if (!B.exact[t]) need = t;
+    } else if (!ext && S.reserve > 0) {
+      // end of the first phase without a trigger: the best model so far becomes the sampling set -- the minimum must be exact
+      const WarpRange WR{B.res, lane};
+      const int a = WR.argmin_first(lo, hi);
+      const double m = B.res[a].nfa;
+      if (m < ac_inf()) {
+        const double g2 = kGuardAbs + kGuardRel * fabs(m);
+        int f = 0x7fffffff;
+        for (int i = lo + lane; i < hi; i += 32)
+          if (!B.exact[i] && B.res[i].nfa <= m + g2) { f = i; break; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+        if (f != 0x7fffffff) need = f;
+      }
+    }
+    if (need >= 0) {
+      D.status = 1; D.it = need;
+      const double* bs = B.basis + static_cast<size_t>(need) * kBasisDoubles;
+      for (int k = 0; k < 4; ++k) D.P[k] = bs[18 + k];
+      D.next = R;
+      if (lane == 0) *B.decide = D;
+      return;
+    }
+  }
+  const WarpRange WR{B.res, lane};
+  const int old_it = S.index_it, old_model = S.index_model;
+  ac_account(S, WR);
+  int pair = R.pair;
+  long long offset = R.offset;
+  int done_all = 0;
+  if (!S.done && (S.index_it != old_it || S.index_model != old_model)) {
+    double* e;
+    int* idx;
+    model_candidates_warp(B, P, B.models + static_cast<size_t>(S.index_it) * 27 + 9 * S.index_model, ws, B.g_e, B.g_i, lane, e, idx);
+    for (int k = lane; k < S.n_index; k += 32) B.vec_index[k] = idx[k];
+  }
+  if (S.done) {
+    const int n_final = ac_final_inliers(S);
+    if (n_final > 0) {
+      double* e;
+      int* idx;
+      model_candidates_warp(B, P, B.models + static_cast<size_t>(S.best_it) * 27 + 9 * S.best_model, ws, B.g_e, B.g_i, lane, e, idx);
+      for (int k = lane; k < n_final; k += 32) B.out_idx[P.m_off + k] = idx[k];
+    }
+    if (lane == 0) { B.out_count[R.pair] = n_final; B.out_iters[R.pair] = S.iter_num; }
+    offset += static_cast<long long>(kSampleF) * S.iter_num;
+    ++pair;
+    if (pair < B.n_pairs) ac_init(S, B.pairs[pair].n, B.max_iterations);
+    else { done_all = 1; if (lane == 0) *B.offset_io = offset; }
+  }
+  __syncwarp();
+  RoundInfo N;
+  N.pair = pair; N.lo = S.iter; N.hi = ac_range_end(S); N.n_index = S.n_index; N.offset = offset; N.done_all = done_all; N.pad = 0;
+  D.status = done_all ? 2 : 0;
+  D.next = N;
+  if (lane == 0) { *B.state = S; *B.round = N; *B.decide = D; }
+}
+
+// Filtered matches of the batch: pair p keeps putative[out_idx[k]] for k < out_count[p], in that (residual) order
+// (geometric_filter.h:87-92).  offsets: exclusive scan of out_count (computed by the host).
+__global__ void __launch_bounds__(256)
+geo_gather_kernel(GeoBatchDev B, const long long* __restrict__ offsets, int2* __restrict__ out) {
+  const GeoPairDev P = B.pairs[blockIdx.x];
+  const int n = B.out_count[blockIdx.x];
+  const long long o = offsets[blockIdx.x];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) out[o + k] = B.matches[P.m_off + B.out_idx[P.m_off + k]];
+}
+
+// ------------------------------------------------------------------------------------------ self-test
+// The scalar core on the device, one thread per case, so that tests can compare its bits with the reference's
+// (tests/test_gpu_geometric.py): 7-point models of a sample, the residual of a probe point under the first model, and one
+// NFA term.
+__global__ void geo_selftest_kernel(int n, const double* __restrict__ x1 /*[n][14]*/, const double* __restrict__ x2, const double* __restrict__ probe /*[n][4]*/,
+                                    double* __restrict__ F /*[n][27]*/, int* __restrict__ n_models, double* __restrict__ err, double* __restrict__ nfa) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double W[81], V[81], a[14], b[14], f[27];
+  for (int k = 0; k < 14; ++k) { a[k] = x1[14 * t + k]; b[k] = x2[14 * t + k]; }
+  for (int k = 0; k < 27; ++k) f[k] = 0.0;
+  const int nm = seven_point_models(a, b, W, V, f);
+  n_models[t] = nm;
+  for (int k = 0; k < 27; ++k) F[27 * t + k] = f[k];
+  const double e = epipolar_error(f, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
+  err[t] = e;
+  nfa[t] = nfa_term(-1.25, 2.5, e, 8 + (t & 63), kSampleF, 3.5f, 1.25f);
+}
+
+}  // namespace geo
+}  // namespace mvgcuda

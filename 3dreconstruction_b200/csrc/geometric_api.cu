@@ -1,0 +1,426 @@
+// geometric_api.cu -- C ABI of the AC-RANSAC geometric filter (include/mvgcuda.h: mvgcuda_geometric_filter), the step of
+// apps/compute_matches right after putative matching (compute_matches.cpp:250-318, geometric_filter.h:37-102).
+// Compiled with -fmad=false: the double-precision arithmetic of the solver must not be contracted into FMAs
+// (acransac_core.cuh).  Host side: per-pair constants that go through the C library's log10 exactly as the reference's do
+// (log-combinatorial tables, logalpha0, loge0), the glibc rand() stream, batching; device side: acransac_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "../../include/mvgcuda.h"
+#include "acransac_kernels.cuh"
+#include "host_util.cuh"
+
+using namespace mvgcuda;
+using namespace mvgcuda::geo;
+
+namespace {
+
+constexpr int kGeoBatchPairs = 1024;        // active pairs per launch
+constexpr long long kGeoBatchMatches = 4ll << 20;
+
+struct GeoState {
+  DevBuf<GeoPairDev> d_pairs;
+  DevBuf<int2> d_matches, d_out;
+  DevBuf<double2> d_x1, d_x2;
+  DevBuf<float> d_logc_pool, d_logc_k;
+  DevBuf<uint32_t> d_stream;
+  DevBuf<IterRes> d_res;
+  DevBuf<double> d_models, d_basis, d_ge;
+  DevBuf<int> d_vec_index, d_gi, d_out_idx, d_out_count, d_out_iters, d_exact;
+  DevBuf<RoundInfo> d_round;
+  DevBuf<AcState> d_state;
+  DevBuf<DecideOut> d_decide;
+  PinnedBuf<DecideOut> h_decide;
+  DevBuf<long long> d_offset, d_offsets;
+  PinnedBuf<GeoPairDev> h_pairs;
+  PinnedBuf<int2> h_matches;
+  PinnedBuf<uint32_t> h_stream;
+  PinnedBuf<int> h_out_count, h_out_iters;
+  PinnedBuf<long long> h_offset, h_offsets;
+  // results of the last call
+  PinnedBuf<int> r_counts;
+  PinnedBuf<long long> r_offsets;
+  PinnedBuf<int> r_matches;
+  // log tables (host copies; the pool only grows within a call)
+  std::vector<float> logc_k;
+  std::vector<float> logc_pool;
+  std::map<int, int> logc_off;  // n -> offset in the pool
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+void geo_free(void* p) {
+  GeoState* G = static_cast<GeoState*>(p);
+  if (!G) return;
+  G->d_pairs.release(); G->d_matches.release(); G->d_out.release(); G->d_x1.release(); G->d_x2.release();
+  G->d_logc_pool.release(); G->d_logc_k.release(); G->d_stream.release(); G->d_res.release(); G->d_models.release(); G->d_ge.release();
+  G->d_vec_index.release(); G->d_gi.release(); G->d_out_idx.release(); G->d_out_count.release(); G->d_out_iters.release();
+  G->d_round.release(); G->d_state.release(); G->d_decide.release(); G->h_decide.release(); G->d_basis.release(); G->d_exact.release();
+  G->d_offset.release(); G->d_offsets.release();
+  G->h_pairs.release(); G->h_matches.release(); G->h_stream.release(); G->h_out_count.release(); G->h_out_iters.release();
+  G->h_offset.release(); G->h_offsets.release(); G->r_counts.release(); G->r_offsets.release(); G->r_matches.release();
+  if (G->ev0) cudaEventDestroy(G->ev0);
+  if (G->ev1) cudaEventDestroy(G->ev1);
+  delete G;
+}
+
+#define GEO_CHECK(ctx, expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      char _b[512];                                                                                       \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      ctx_set_error(ctx, _b);                                                                             \
+      return _e == cudaErrorMemoryAllocation ? MVGCUDA_ERR_NOMEM : MVGCUDA_ERR_CUDA;                      \
+    }                                                                                                     \
+  } while (0)
+
+int fail(mvgcuda_ctx* ctx, const char* msg) {
+  ctx_set_error(ctx, msg);
+  return MVGCUDA_ERR_INVALID;
+}
+
+}  // namespace
+
+extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double precision, int iterations, unsigned seed, int64_t n_pairs,
+                                        const int32_t* pairs, const int32_t* counts, const int64_t* offsets, const int32_t* matches,
+                                        const int32_t* image_sizes, mvgcuda_pair_matches* out) try {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !counts || !offsets || !matches)) || !image_sizes) return fail(ctx, "geometric_filter: null argument");
+  if (model != 'f') return fail(ctx, "geometric_filter: only the fundamental-matrix model ('f') is built (SURVEY.md 8(f)-1)");
+  if (iterations < 10 || iterations > (1 << 20)) return fail(ctx, "geometric_filter: iterations out of range");
+  const CtxView V = ctx_view(ctx);
+  if (!V.feats) return fail(ctx, "geometric_filter: call mvgcuda_set_features (or stream the features) first");
+  GEO_CHECK(ctx, cudaSetDevice(V.device));
+  if (!*V.geo) {
+    *V.geo = new GeoState();
+    *V.geo_free = geo_free;
+  }
+  GeoState& G = *static_cast<GeoState*>(*V.geo);
+  if (!G.ev0) { GEO_CHECK(ctx, cudaEventCreate(&G.ev0)); GEO_CHECK(ctx, cudaEventCreate(&G.ev1)); }
+  cudaStream_t st = V.stream;
+  int rc = ctx_wait_uploads(ctx);
+  if (rc) return rc;
+
+  // ---- validate, find the active pairs (ACRANSAC returns at once, drawing nothing, unless nData > 7: estimator_acransac.h:137-138)
+  std::vector<int64_t> active;
+  int n_max = 0;
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const int i = pairs[2 * p], j = pairs[2 * p + 1];
+    if (i < 0 || j < 0 || i >= V.n_images || j >= V.n_images || counts[p] < 0) return fail(ctx, "geometric_filter: bad pair / count");
+    for (int k = 0; k < counts[p]; ++k) {
+      const int32_t* m = matches + 2 * (offsets[p] + k);
+      if (m[0] < 0 || m[0] >= V.rows[i] || m[1] < 0 || m[1] >= V.rows[j]) return fail(ctx, "geometric_filter: match index out of range");
+    }
+    if (counts[p] > kSampleF) { active.push_back(p); n_max = std::max(n_max, counts[p]); }
+  }
+  GEO_CHECK(ctx, G.r_counts.reserve(std::max<int64_t>(n_pairs, 1)));
+  GEO_CHECK(ctx, G.r_offsets.reserve(n_pairs + 1));
+  GEO_CHECK(ctx, G.r_matches.reserve(2));
+  for (int64_t p = 0; p < n_pairs; ++p) G.r_counts.p[p] = 0;
+
+  // ---- log tables through the C library's log10, accumulated exactly as logcombi does (estimator_acransac.h:39-65)
+  if ((int)G.logc_k.size() < n_max + 1) {
+    G.logc_k.resize(n_max + 1);
+    make_logc_k(kSampleF, n_max, G.logc_k.data());
+  }
+  G.logc_pool.clear();
+  G.logc_off.clear();
+  for (int64_t p : active) {
+    const int n = counts[p];
+    if (G.logc_off.count(n)) continue;
+    const int off = (int)G.logc_pool.size();
+    G.logc_off[n] = off;
+    G.logc_pool.resize(off + n + 1);
+    make_logc_n(n, G.logc_pool.data() + off);
+  }
+  if (!active.empty()) {
+    GEO_CHECK(ctx, G.d_logc_k.reserve(G.logc_k.size()));
+    GEO_CHECK(ctx, G.d_logc_pool.reserve(std::max<size_t>(G.logc_pool.size(), 1)));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_logc_k.p, G.logc_k.data(), G.logc_k.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_logc_pool.p, G.logc_pool.data(), G.logc_pool.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+
+  // ---- scratch: one warp per iteration of a range (at most `iterations` of them) + the accounting warp
+  int n_cap = 32;
+  while (n_cap < n_max) n_cap <<= 1;
+  const size_t max_warps = (size_t)((iterations + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
+  if (!active.empty()) {
+    GEO_CHECK(ctx, G.d_res.reserve(iterations + 8));
+    GEO_CHECK(ctx, G.d_models.reserve((size_t)(iterations + 8) * 27));
+    GEO_CHECK(ctx, G.d_basis.reserve((size_t)(iterations + 8) * kBasisDoubles));
+    GEO_CHECK(ctx, G.d_exact.reserve(iterations + 8));
+    GEO_CHECK(ctx, G.d_vec_index.reserve(n_max));
+    GEO_CHECK(ctx, G.d_ge.reserve((max_warps + 1) * n_cap));
+    GEO_CHECK(ctx, G.d_gi.reserve((max_warps + 1) * n_cap));
+    GEO_CHECK(ctx, G.d_round.reserve(1));
+    GEO_CHECK(ctx, G.d_state.reserve(1));
+    GEO_CHECK(ctx, G.d_decide.reserve(1));
+    GEO_CHECK(ctx, G.h_decide.reserve(1));
+    GEO_CHECK(ctx, G.d_offset.reserve(1));
+    GEO_CHECK(ctx, G.h_offset.reserve(1));
+  }
+  long long exact_requests = 0, rounds = 0;
+
+  // ---- the process-wide rand() stream: srand(seed) here, consumed pair after pair (the reference never seeds: seed 1)
+  GlibcRand gen;
+  glibc_srand(gen, seed);
+  long long gen_pos = 0;   // values generated so far
+  long long offset = 0;    // values the pairs processed so far have consumed
+  std::vector<uint32_t> window;  // stream values [win_base, gen_pos)
+  long long win_base = 0;
+  float gpu_ms = 0.f;
+  int launches = 0;
+
+  std::vector<std::vector<int32_t> > kept(active.size());  // filtered matches of the active pairs
+  size_t a0 = 0;
+  while (a0 < active.size()) {
+    size_t a1 = a0;
+    long long tot = 0;
+    while (a1 < active.size() && (a1 - a0) < (size_t)kGeoBatchPairs) {
+      const long long c = counts[active[a1]];
+      if (a1 > a0 && tot + c > kGeoBatchMatches) break;
+      tot += c;
+      ++a1;
+    }
+    const int nb = (int)(a1 - a0);
+    GEO_CHECK(ctx, G.h_pairs.reserve(nb));
+    GEO_CHECK(ctx, G.h_matches.reserve(tot));
+    GEO_CHECK(ctx, G.d_pairs.reserve(nb));
+    GEO_CHECK(ctx, G.d_matches.reserve(tot));
+    GEO_CHECK(ctx, G.d_x1.reserve(tot));
+    GEO_CHECK(ctx, G.d_x2.reserve(tot));
+    GEO_CHECK(ctx, G.d_out_idx.reserve(tot));
+    GEO_CHECK(ctx, G.d_out.reserve(tot));
+    GEO_CHECK(ctx, G.d_out_count.reserve(nb));
+    GEO_CHECK(ctx, G.d_out_iters.reserve(nb));
+    GEO_CHECK(ctx, G.d_offsets.reserve(nb + 1));
+    GEO_CHECK(ctx, G.h_out_count.reserve(nb));
+    GEO_CHECK(ctx, G.h_out_iters.reserve(nb));
+    GEO_CHECK(ctx, G.h_offsets.reserve(nb + 1));
+    long long mo = 0;
+    for (int k = 0; k < nb; ++k) {
+      const int64_t p = active[a0 + k];
+      const int i = pairs[2 * p], j = pairs[2 * p + 1];
+      GeoPairDev D;
+      D.n = counts[p];
+      D.m_off = (int)mo;
+      D.row0_i = V.row0[i];
+      D.row0_j = V.row0[j];
+      D.logc_off = G.logc_off[D.n];
+      D.out_slot = (int)p;
+      const int wi = image_sizes[2 * i], hi = image_sizes[2 * i + 1], wj = image_sizes[2 * j], hj = image_sizes[2 * j + 1];
+      D.N1 = make_normalizer(wi, hi);
+      D.N2 = make_normalizer(wj, hj);
+      // estimator_acransac.h:140-142, estimator_acransac_kernel_adaptator.h:53-58, estimator_acransac.h:153
+      D.max_threshold = std::isinf(precision) ? precision : precision * D.N2.d * D.N2.d;
+      const double diag = sqrt(wj * (double)wj + hj * (double)hj);
+      const double area = wj * (double)hj;
+      D.logalpha0 = log10(2.0 * diag / area / D.N2.d);
+      D.loge0 = log10((double)kMaxModelsF * (size_t)(D.n - kSampleF));
+      G.h_pairs.p[k] = D;
+      for (int q = 0; q < D.n; ++q) {
+        const int32_t* m = matches + 2 * (offsets[p] + q);
+        G.h_matches.p[mo + q] = make_int2(m[0], m[1]);
+      }
+      mo += D.n;
+    }
+    // stream window [offset, offset + 7 * iterations * nb)
+    const long long need_end = offset + (long long)kSampleF * iterations * nb;
+    if (offset > win_base) {
+      window.erase(window.begin(), window.begin() + (size_t)(offset - win_base));
+      win_base = offset;
+    }
+    window.reserve((size_t)(need_end - win_base));
+    while (gen_pos < need_end) { window.push_back(glibc_rand(gen)); ++gen_pos; }
+    const size_t n_stream = (size_t)(need_end - offset);
+    GEO_CHECK(ctx, G.h_stream.reserve(n_stream));
+    GEO_CHECK(ctx, G.d_stream.reserve(n_stream));
+    memcpy(G.h_stream.p, window.data() + (size_t)(offset - win_base), n_stream * sizeof(uint32_t));
+    G.h_offset.p[0] = offset;
+
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_pairs.p, G.h_pairs.p, nb * sizeof(GeoPairDev), cudaMemcpyHostToDevice, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_matches.p, G.h_matches.p, tot * sizeof(int2), cudaMemcpyHostToDevice, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_stream.p, G.h_stream.p, n_stream * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_offset.p, G.h_offset.p, sizeof(long long), cudaMemcpyHostToDevice, st));
+    GEO_CHECK(ctx, cudaEventRecord(G.ev0, st));
+
+    GeoBatchDev B;
+    B.pairs = G.d_pairs.p; B.n_pairs = nb; B.matches = G.d_matches.p; B.feats = V.feats; B.x1 = G.d_x1.p; B.x2 = G.d_x2.p;
+    B.logc_pool = G.d_logc_pool.p; B.logc_k = G.d_logc_k.p; B.stream = G.d_stream.p; B.stream_base = offset;
+    B.max_iterations = iterations; B.res = G.d_res.p; B.models = G.d_models.p; B.vec_index = G.d_vec_index.p;
+    B.g_e = G.d_ge.p; B.g_i = G.d_gi.p; B.n_cap = n_cap; B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p;
+    B.out_iters = G.d_out_iters.p; B.round = G.d_round.p; B.state = G.d_state.p; B.offset_io = G.d_offset.p;
+    B.basis = G.d_basis.p; B.exact = G.d_exact.p; B.decide = G.d_decide.p;
+    geo_prep_kernel<<<nb, 256, 0, st>>>(B);
+    GEO_CHECK(ctx, cudaGetLastError());
+    // The chain of pairs: evaluate a range (one warp per iteration) -> account for it (one warp) -> whatever the
+    // accounting asks for: roots of one cubic from THIS machine's C library, the next range, or the next pair.
+    geo_decide_kernel<<<1, 32, 0, st>>>(B, 1);
+    GEO_CHECK(ctx, cudaGetLastError());
+    launches += 2;
+    for (;;) {
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p, G.d_decide.p, sizeof(DecideOut), cudaMemcpyDeviceToHost, st));
+      GEO_CHECK(ctx, cudaStreamSynchronize(st));
+      const DecideOut D = G.h_decide.p[0];
+      if (D.status == 2) break;
+      if (D.status == 1) {
+        double roots[3] = {0.0, 0.0, 0.0};
+        const int nr = solve_cubic(D.P, roots);  // host libm: acos / cos / pow as the reference's process would call them
+        geo_exact_kernel<<<1, 32, 0, st>>>(B, D.it, nr, roots[0], roots[1], roots[2]);
+        GEO_CHECK(ctx, cudaGetLastError());
+        ++exact_requests;
+        ++launches;
+      } else {
+        const int n_it = D.next.hi - D.next.lo;
+        if (n_it > 0) {
+          geo_eval_kernel<<<(n_it + kEvalWarps - 1) / kEvalWarps, 32 * kEvalWarps, 0, st>>>(B);
+          GEO_CHECK(ctx, cudaGetLastError());
+          ++launches;
+        }
+        ++rounds;
+      }
+      geo_decide_kernel<<<1, 32, 0, st>>>(B, 0);
+      GEO_CHECK(ctx, cudaGetLastError());
+      ++launches;
+    }
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_count.p, G.d_out_count.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_iters.p, G.d_out_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GEO_CHECK(ctx, cudaMemcpyAsync(G.h_offset.p, G.d_offset.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GEO_CHECK(ctx, cudaStreamSynchronize(st));
+    long long kept_total = 0;
+    for (int k = 0; k < nb; ++k) { G.h_offsets.p[k] = kept_total; kept_total += G.h_out_count.p[k]; }
+    G.h_offsets.p[nb] = kept_total;
+    if (kept_total > 0) {
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_offsets.p, G.h_offsets.p, (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+      geo_gather_kernel<<<nb, 256, 0, st>>>(B, G.d_offsets.p, G.d_out.p);
+      GEO_CHECK(ctx, cudaGetLastError());
+      GEO_CHECK(ctx, G.h_matches.reserve(kept_total));
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.h_matches.p, G.d_out.p, kept_total * sizeof(int2), cudaMemcpyDeviceToHost, st));
+      ++launches;
+    }
+    GEO_CHECK(ctx, cudaEventRecord(G.ev1, st));
+    GEO_CHECK(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    GEO_CHECK(ctx, cudaEventElapsedTime(&ms, G.ev0, G.ev1));
+    gpu_ms += ms;
+    for (int k = 0; k < nb; ++k) {
+      const int c = G.h_out_count.p[k];
+      std::vector<int32_t>& dst = kept[a0 + k];
+      dst.resize((size_t)2 * c);
+      for (int q = 0; q < c; ++q) {
+        const int2 m = G.h_matches.p[G.h_offsets.p[k] + q];
+        dst[2 * q] = m.x; dst[2 * q + 1] = m.y;
+      }
+    }
+    offset = G.h_offset.p[0];
+    a0 = a1;
+  }
+
+  // ---- results in the caller's pair order
+  long long total = 0;
+  for (size_t a = 0; a < active.size(); ++a) G.r_counts.p[active[a]] = (int)(kept[a].size() / 2);
+  for (int64_t p = 0; p < n_pairs; ++p) { G.r_offsets.p[p] = total; total += G.r_counts.p[p]; }
+  G.r_offsets.p[n_pairs] = total;
+  GEO_CHECK(ctx, G.r_matches.reserve((size_t)std::max<long long>(total, 1) * 2));
+  for (size_t a = 0; a < active.size(); ++a)
+    if (!kept[a].empty()) memcpy(G.r_matches.p + 2 * G.r_offsets.p[active[a]], kept[a].data(), kept[a].size() * sizeof(int32_t));
+  if (out) {
+    out->n_pairs = n_pairs;
+    out->counts = G.r_counts.p;
+    out->offsets = reinterpret_cast<const int64_t*>(G.r_offsets.p);
+    out->matches = G.r_matches.p;
+    out->gpu_ms = gpu_ms;
+    out->knn_kernel_ms = 0.f;
+    out->knn_kernel_launches = (int32_t)std::min<long long>(exact_requests, 0x7fffffff);  // models re-evaluated with host roots
+    out->total_launches = launches;
+    out->rescanned_queries = offset;  // rand() values the filter consumed (the reference's stream position afterwards)
+  }
+  return MVGCUDA_OK;
+} catch (const std::bad_alloc&) {
+  if (ctx) ctx_set_error(ctx, "out of host memory");
+  return MVGCUDA_ERR_NOMEM;
+} catch (...) {
+  if (ctx) ctx_set_error(ctx, "unexpected exception");
+  return MVGCUDA_ERR_INVALID;
+}
+
+// Instrumentation: the scalar solver core on the device (one thread per case), for bit comparisons in the tests.
+extern "C" int mvgcuda_geo_selftest(mvgcuda_ctx* ctx, int n, const double* x1, const double* x2, const double* probe, double* F,
+                                    int32_t* n_models, double* err, double* nfa) try {
+  if (!ctx || n < 1 || !x1 || !x2 || !probe || !F || !n_models || !err || !nfa) return MVGCUDA_ERR_INVALID;
+  const CtxView V = ctx_view(ctx);
+  GEO_CHECK(ctx, cudaSetDevice(V.device));
+  DevBuf<double> d_x1, d_x2, d_p, d_F, d_e, d_n;
+  DevBuf<int> d_nm;
+  auto cleanup = [&]() { d_x1.release(); d_x2.release(); d_p.release(); d_F.release(); d_e.release(); d_n.release(); d_nm.release(); };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = d_x1.reserve((size_t)n * 14);
+  if (e == cudaSuccess) e = d_x2.reserve((size_t)n * 14);
+  if (e == cudaSuccess) e = d_p.reserve((size_t)n * 4);
+  if (e == cudaSuccess) e = d_F.reserve((size_t)n * 27);
+  if (e == cudaSuccess) e = d_e.reserve(n);
+  if (e == cudaSuccess) e = d_n.reserve(n);
+  if (e == cudaSuccess) e = d_nm.reserve(n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x1.p, x1, (size_t)n * 14 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x2.p, x2, (size_t)n * 14 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_p.p, probe, (size_t)n * 4 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    geo_selftest_kernel<<<(n + 63) / 64, 64>>>(n, d_x1.p, d_x2.p, d_p.p, d_F.p, d_nm.p, d_e.p, d_n.p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(F, d_F.p, (size_t)n * 27 * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(n_models, d_nm.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(err, d_e.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(nfa, d_n.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cleanup();
+  GEO_CHECK(ctx, e);
+  return MVGCUDA_OK;
+} catch (...) {
+  return MVGCUDA_ERR_NOMEM;
+}
+
+// Write n_pairs match lists in the reference's text format, pairs with no match omitted == PairedIndexedMatchToStream over a
+// PairWiseMatches map that only holds non-empty entries (geometric_filter.h:85-98, indexed_match_utils.h:22-38).  `pairs`
+// must be in lexicographic (i, j) order (std::map iteration order).
+extern "C" int mvgcuda_write_matches(const char* path, int64_t n_pairs, const int32_t* pairs, const int32_t* counts, const int64_t* offsets,
+                                     const int32_t* matches, int skip_empty) try {
+  if (!path || n_pairs < 0 || (n_pairs > 0 && (!pairs || !counts || !offsets || !matches))) return MVGCUDA_ERR_INVALID;
+  FILE* f = fopen(path, "wb");
+  if (!f) return MVGCUDA_ERR_IO;
+  std::vector<char> buf(1 << 22);
+  size_t used = 0;
+  auto put_int = [&](int v, char sep) {
+    char tmp[12];
+    int n = 0;
+    unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) buf[used++] = '-';
+    while (n) buf[used++] = tmp[--n];
+    buf[used++] = sep;
+  };
+  bool ok = true;
+  for (int64_t p = 0; p < n_pairs && ok; ++p) {
+    if (skip_empty && counts[p] == 0) continue;
+    if (used + 64 > buf.size()) { ok = fwrite(buf.data(), 1, used, f) == used; used = 0; }
+    put_int(pairs[2 * p], ' ');
+    put_int(pairs[2 * p + 1], '\n');
+    put_int(counts[p], '\n');
+    const int32_t* m = matches + 2 * offsets[p];
+    for (int c = 0; c < counts[p] && ok; ++c) {
+      if (used + 64 > buf.size()) { ok = fwrite(buf.data(), 1, used, f) == used; used = 0; }
+      put_int(m[2 * c], ' ');
+      put_int(m[2 * c + 1], '\n');
+    }
+  }
+  ok = ok && fwrite(buf.data(), 1, used, f) == used;
+  if (fclose(f) != 0 || !ok) return MVGCUDA_ERR_IO;
+  return MVGCUDA_OK;
+} catch (...) {
+  return MVGCUDA_ERR_NOMEM;
+}

@@ -22,6 +22,7 @@
 
 #include "../../include/mvgcuda.h"
 #include "kernels.cuh"
+#include "host_util.cuh"
 
 namespace mvgcuda {
 
@@ -35,50 +36,6 @@ static thread_local char g_create_error[512] = "";
       return _e == cudaErrorMemoryAllocation ? MVGCUDA_ERR_NOMEM : MVGCUDA_ERR_CUDA;                \
     }                                                                                               \
   } while (0)
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;  // elements
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-template <typename T>
-struct PinnedBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  // grow, preserving the first `keep` elements
-  cudaError_t reserve(size_t n, size_t keep = 0) {
-    if (n <= cap) return cudaSuccess;
-    size_t ncap = std::max(n, cap + cap / 2);
-    T* np = nullptr;
-    cudaError_t e = cudaMallocHost(&np, ncap * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (keep) memcpy(np, p, keep * sizeof(T));
-    if (p) cudaFreeHost(p);
-    p = np;
-    cap = ncap;
-    return cudaSuccess;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
 
 constexpr float kDefaultPruneRho = 0.8f;
 constexpr int kDefaultRescanRows = 1 << 20;  // 128 MB of gathered queries per second pass
@@ -189,6 +146,9 @@ struct mvgcuda_ctx {
   int64_t r_pairs = 0;
 
   cudaEvent_t ev[2] = {nullptr, nullptr};
+
+  void* geo = nullptr;               // state of the geometric-filter unit (geometric_api.cu)
+  void (*geo_free)(void*) = nullptr;
 
   void set_error(const char* fmt, ...) {
     va_list ap;
@@ -835,6 +795,24 @@ static int knn2_impl(mvgcuda_ctx* ctx, const Arena& A, int db_img, const Arena& 
     return MVGCUDA_ERR_INVALID;                                                                            \
   }
 
+namespace mvgcuda {
+CtxView ctx_view(mvgcuda_ctx* ctx) {
+  CtxView v;
+  v.device = ctx->device;
+  v.sm_count = ctx->prop.multiProcessorCount;
+  v.stream = ctx->stream;
+  v.feats = ctx->images.has_feats ? ctx->images.feat.p : nullptr;
+  v.row0 = ctx->images.row0.data();
+  v.rows = ctx->images.rows.data();
+  v.n_images = (int)ctx->images.rows.size();
+  v.geo = &ctx->geo;
+  v.geo_free = &ctx->geo_free;
+  return v;
+}
+void ctx_set_error(mvgcuda_ctx* ctx, const char* msg) { ctx->set_error("%s", msg); }
+int ctx_wait_uploads(mvgcuda_ctx* ctx) { return wait_for_all_images(ctx, ctx->images); }
+}  // namespace mvgcuda
+
 extern "C" {
 
 int mvgcuda_version(void) { return 200; }
@@ -911,6 +889,7 @@ void mvgcuda_destroy(mvgcuda_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->geo && ctx->geo_free) ctx->geo_free(ctx->geo);
   ctx->images.release();
   ctx->scratch.release();
   for (BatchSlot& S : ctx->slot) S.release();

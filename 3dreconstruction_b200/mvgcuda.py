@@ -90,6 +90,10 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_set_features": (C.c_int, [_ctx, C.c_int, _f32pp, _i32p]),
     "mvgcuda_match_collection": (C.c_int, [_ctx, C.c_int64, _i32p, C.c_float, C.c_int, C.POINTER(_PairMatches)]),
     "mvgcuda_export_matches": (C.c_int, [_ctx, _i32p, C.c_char_p]),
+    "mvgcuda_geometric_filter": (C.c_int, [_ctx, C.c_char, C.c_double, C.c_int, C.c_uint, C.c_int64, _i32p, _i32p, C.POINTER(C.c_int64), _i32p,
+                                           _i32p, C.POINTER(_PairMatches)]),
+    "mvgcuda_geo_selftest": (C.c_int, [_ctx, C.c_int] + [C.POINTER(C.c_double)] * 4 + [_i32p] + [C.POINTER(C.c_double)] * 2),
+    "mvgcuda_write_matches": (C.c_int, [C.c_char_p, C.c_int64, _i32p, _i32p, C.POINTER(C.c_int64), _i32p, C.c_int]),
     "mvgcuda_get_device_info": (C.c_int, [_ctx, C.POINTER(_DeviceInfo)]),
     "mvgcuda_probe_i8_peak": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), _f32p]),
 }
@@ -139,6 +143,22 @@ def upload_friendly_order(pairs: np.ndarray) -> np.ndarray:
     return pairs[np.lexsort((lo, hi))]
 
 
+def write_matches(path: str, res: "PairMatches", skip_empty: bool = False) -> None:
+    """PairedIndexedMatchToStream (indexed_match_utils.h:22-38) of a result whose pairs are in (i, j) order; skip_empty drops
+    pairs without matches, as the reference's geometric map never receives them (geometric_filter.h:85-98)."""
+    lib = load_library()
+    pairs = np.ascontiguousarray(res.pairs, dtype=np.int32).reshape(-1, 2)
+    counts = np.ascontiguousarray(res.counts, dtype=np.int32)
+    offsets = np.ascontiguousarray(res.offsets, dtype=np.int64)
+    matches = np.ascontiguousarray(res.matches, dtype=np.int32).reshape(-1, 2)
+    if len(matches) == 0:
+        matches = np.zeros((1, 2), np.int32)
+    rc = lib.mvgcuda_write_matches(path.encode(), len(pairs), pairs.ctypes.data_as(_i32p), counts.ctypes.data_as(_i32p),
+                                   offsets.ctypes.data_as(C.POINTER(C.c_int64)), matches.ctypes.data_as(_i32p), int(skip_empty))
+    if rc != 0:
+        raise MvgCudaError(f"mvgcuda_write_matches({path}) failed [{rc}]")
+
+
 def _as_u8_matrix(a: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint8)
     if a.ndim != 2 or a.shape[1] != DIM:
@@ -158,6 +178,17 @@ class PairMatches:
     def pair(self, p: int) -> np.ndarray:
         """[count][2] (_i, _j) of pair p."""
         return self.matches[self.offsets[p]:self.offsets[p] + self.counts[p]]
+
+    @staticmethod
+    def from_dict(pairwise: Dict[Tuple[int, int], np.ndarray]) -> "PairMatches":
+        """From a PairWiseMatches-like dict (e.g. io.matches_from_text of an imported matches.putative.txt), in std::map order."""
+        keys = sorted(pairwise)
+        pairs = np.array(keys, np.int32).reshape(-1, 2)
+        counts = np.array([len(pairwise[k]) for k in keys], np.int32)
+        offsets = np.zeros(len(keys) + 1, np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        matches = (np.concatenate([np.asarray(pairwise[k], np.int32).reshape(-1, 2) for k in keys]) if keys else np.zeros((0, 2), np.int32))
+        return PairMatches(pairs, counts, offsets, matches.astype(np.int32), {})
 
     def as_dict(self) -> Dict[Tuple[int, int], np.ndarray]:
         """PairWiseMatches (indexed_match.h:69): first insertion wins for duplicate keys, as std::map::insert."""
@@ -327,6 +358,41 @@ class Context:
         self._check(self._lib.mvgcuda_match_collection(self._h, len(pairs), pairs.ctypes.data_as(_i32p), C.c_float(ratio_sq),
                                                        host_threads, C.byref(pm)), "mvgcuda_match_collection")
         return self._collect(pairs, pm) if collect else pm
+
+    # -- the step after the path: AC-RANSAC geometric filter (geometric_filter.h:37-102)
+    def geometric_filter(self, putative: "PairMatches", image_sizes: Sequence[Tuple[int, int]], model: str = "f", precision: float = 4.0,
+                         iterations: int = 4096, seed: int = 1) -> "PairMatches":
+        """ImageCollectionGeometricFilter::Filter(GeometricFilter_FMatrix_AC(precision, iterations)) over `putative` (pairs in
+        std::map order; features already set).  seed=1 is the reference's never-seeded rand() stream.  Returns the kept
+        matches per pair in ascending-residual order; timing['rand_consumed'] = rand() values drawn."""
+        pairs = np.ascontiguousarray(putative.pairs, dtype=np.int32).reshape(-1, 2)
+        counts = np.ascontiguousarray(putative.counts, dtype=np.int32)
+        offsets = np.ascontiguousarray(putative.offsets, dtype=np.int64)
+        matches = np.ascontiguousarray(putative.matches, dtype=np.int32).reshape(-1, 2)
+        if len(matches) == 0:
+            matches = np.zeros((1, 2), np.int32)
+        sizes = np.ascontiguousarray(image_sizes, dtype=np.int32).reshape(-1, 2)
+        pm = _PairMatches()
+        self._check(self._lib.mvgcuda_geometric_filter(self._h, model.encode()[:1], C.c_double(precision), int(iterations), C.c_uint(seed),
+                                                       len(pairs), pairs.ctypes.data_as(_i32p), counts.ctypes.data_as(_i32p),
+                                                       offsets.ctypes.data_as(C.POINTER(C.c_int64)), matches.ctypes.data_as(_i32p),
+                                                       sizes.ctypes.data_as(_i32p), C.byref(pm)), "mvgcuda_geometric_filter")
+        res = self._collect(pairs, pm)
+        res.timing["rand_consumed"] = res.timing.pop("rescanned_queries")
+        return res
+
+    def geo_selftest(self, x1: np.ndarray, x2: np.ndarray, probe: np.ndarray):
+        """Device bits of the solver core: (F [n][27], n_models [n], residual [n], nfa term [n])."""
+        x1 = np.ascontiguousarray(x1, np.float64).reshape(-1, 14)
+        x2 = np.ascontiguousarray(x2, np.float64).reshape(-1, 14)
+        probe = np.ascontiguousarray(probe, np.float64).reshape(-1, 4)
+        n = len(x1)
+        F = np.zeros((n, 27)); nm = np.zeros(n, np.int32); err = np.zeros(n); nfa = np.zeros(n)
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.mvgcuda_geo_selftest(self._h, n, x1.ctypes.data_as(dp), x2.ctypes.data_as(dp), probe.ctypes.data_as(dp),
+                                                   F.ctypes.data_as(dp), nm.ctypes.data_as(_i32p), err.ctypes.data_as(dp), nfa.ctypes.data_as(dp)),
+                    "mvgcuda_geo_selftest")
+        return F, nm, err, nfa
 
     def export_matches(self, pairs: np.ndarray, path: str) -> None:
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)

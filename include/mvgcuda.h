@@ -200,7 +200,39 @@ int mvgcuda_match_collection(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* p
 int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* path);
 
 /* ------------------------------------------------------------------------------------------
+ * Geometric filter: the step of apps/compute_matches right after putative matching (compute_matches.cpp:250-318) ==
+ * ImageCollectionGeometricFilter<ScalePointFeature>::Filter(GeometricFilter_FMatrix_AC(precision, iterations), putatives,
+ * geometric, image sizes)  (geometric_filter.h:37-102, fundamental_acransac.h:13-57): per pair an a-contrario RANSAC
+ * (ACRANSAC, estimator_acransac.h:125-245) over the 7-point fundamental-matrix solver
+ * (solver_fundamental_kernel.cpp:11-66), point-to-epipolar-line residuals, upper bound `precision` pixels (4.0 in
+ * compute_matches.cpp:254), `iterations` = 4096 (fundamental_acransac.h:18); pairs whose model is not meaningful or has
+ * fewer than 2.5 x 7 inliers come back empty.  On the GPU the control flow, the sample stream (glibc rand(), `seed` = 1 ==
+ * the reference's never-seeded default, consumed pair after pair in the given order) and the double-precision arithmetic
+ * of the solver are the reference's; see DESIGN.md for what is bit-exact and what is not.
+ *   model        'f' (the homography / essential variants are not built)
+ *   pairs/counts/offsets/matches   the putative matches, laid out like mvgcuda_pair_matches (e.g. the result of
+ *                mvgcuda_match_collection, or an imported matches.putative.txt); pairs in std::map order
+ *   image_sizes  [n_images][2] = width, height of every uploaded image (lists.txt columns 2, 3)
+ * The feature coordinates must have been set (mvgcuda_set_features / mvgcuda_stream_image).  The result (matches of every
+ * pair in ascending-residual order, as the reference stores them) is owned by the context and valid until the next
+ * geometric_filter / destroy; out->rescanned_queries holds the number of rand() values consumed. */
+int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double precision, int iterations, unsigned seed,
+                             int64_t n_pairs, const int32_t* pairs, const int32_t* counts, const int64_t* offsets,
+                             const int32_t* matches, const int32_t* image_sizes, mvgcuda_pair_matches* out);
+
+/* "i j\ncount\n_i _j\n..." for the given lists (PairedIndexedMatchToStream, indexed_match_utils.h:22-38); skip_empty != 0
+ * omits pairs without matches, as a PairWiseMatches map that never received them does (geometric_filter.h:85-98). */
+int mvgcuda_write_matches(const char* path, int64_t n_pairs, const int32_t* pairs, const int32_t* counts,
+                          const int64_t* offsets, const int32_t* matches, int skip_empty);
+
+/* ------------------------------------------------------------------------------------------
  * Instrumentation. */
+/* The geometric filter's scalar solver core run on the device, one thread per case: x1/x2 [n][7][2] sampled (normalised)
+ * correspondences -> F [n][3][9] models + their number; probe [n][4] = (x1, y1, x2, y2) -> residual under the first
+ * model; nfa = one NFA term on that residual.  Lets the tests compare device bits with the reference's. */
+int mvgcuda_geo_selftest(mvgcuda_ctx* ctx, int n, const double* x1, const double* x2, const double* probe, double* F,
+                         int32_t* n_models, double* err, double* nfa);
+
 typedef struct mvgcuda_device_info {
   char name[128];
   int sm_count;

@@ -71,4 +71,90 @@ int ref_geometric_filter(const char* match_dir, const char* names, const int* si
   return (int)geometric.size();
 }
 
+// ---- entry points for the unit tests of the restatement (tests/native/test_acransac_core.cpp, tests/test_oracle.py) ----
+
+// SevenPointSolver::Solve on 7 correspondences ([7][2] each); F: up to 3 models, row-major 3x3.  Returns the model count.
+int ref_seven_point(const double* x1, const double* x2, double* F) {
+  Mat a(2, 7), b(2, 7);
+  for (int i = 0; i < 7; ++i) { a(0, i) = x1[2 * i]; a(1, i) = x1[2 * i + 1]; b(0, i) = x2[2 * i]; b(1, i) = x2[2 * i + 1]; }
+  std::vector<Mat3> models;
+  fundamental::SevenPointSolver::Solve(a, b, &models);
+  for (size_t k = 0; k < models.size(); ++k)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) F[9 * k + 3 * r + c] = models[k](r, c);
+  return (int)models.size();
+}
+
+// NormalizePoints(points, &out, &T, width, height) on n float points ([n][2]); T: row-major 3x3.
+void ref_normalize(const float* pts, int n, int width, int height, double* out, double* T) {
+  Mat x(2, n), xn;
+  for (int i = 0; i < n; ++i) x.col(i) = Vec2f(pts[2 * i], pts[2 * i + 1]).cast<double>();
+  Mat3 N;
+  NormalizePoints(x, &xn, &N, width, height);
+  for (int i = 0; i < n; ++i) { out[2 * i] = xn(0, i); out[2 * i + 1] = xn(1, i); }
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T[3 * r + c] = N(r, c);
+}
+
+double ref_epipolar_error(const double* F, double x1, double y1, double x2, double y2) {
+  Mat3 M;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M(r, c) = F[3 * r + c];
+  return fundamental::SimpleError::Error(M, Vec2(x1, y1), Vec2(x2, y2));
+}
+
+void ref_rand(unsigned seed, int n, unsigned* out) {
+  srand(seed);
+  for (int i = 0; i < n; ++i) out[i] = (unsigned)rand();
+}
+
+void ref_random_sample7(unsigned seed, int skip, int n, int* out) {
+  srand(seed);
+  for (int i = 0; i < skip; ++i) rand();
+  std::vector<size_t> s;
+  RandomSample(7, (size_t)n, &s);
+  for (int i = 0; i < 7; ++i) out[i] = (int)s[i];
+}
+
+void ref_logc(int n, float* logc_n, float* logc_k) {
+  std::vector<float> a, b;
+  makelogcombi_n((size_t)n, a);
+  makelogcombi_k(7, (size_t)n, b);
+  for (int k = 0; k <= n; ++k) { logc_n[k] = a[k]; logc_k[k] = b[k]; }
+}
+
+// One pair through the reference's own kernel + ACRANSAC (fundamental_acransac.h:23-47 without the final 2.5 x 7 floor):
+// xI, xJ [n][2] float feature coordinates.  inliers: capacity n.  out[0] = errorMax, out[1] = minNFA, out[2] = rand() calls
+// consumed (counted by re-running the stream).  Returns the number of inliers.
+int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                   unsigned seed, int* inliers, double* out) {
+  Mat a(2, n), b(2, n);
+  for (int i = 0; i < n; ++i) {
+    a.col(i) = Vec2f(xI[2 * i], xI[2 * i + 1]).cast<double>();
+    b.col(i) = Vec2f(xJ[2 * i], xJ[2 * i + 1]).cast<double>();
+  }
+  typedef ACKernelAdaptor<fundamental::SevenPointSolver, fundamental::SimpleError, UnnormalizerT, Mat3> KernelType;
+  KernelType kernel(a, wI, hI, b, wJ, hJ, true);
+  std::vector<size_t> vec_inliers;
+  Mat3 F;
+  srand(seed);
+  std::pair<double, double> r = ACRANSAC(kernel, vec_inliers, (size_t)iterations, &F, precision);
+  // how far the stream moved: find the position whose next value equals what rand() returns now
+  const unsigned next = (unsigned)rand();
+  srand(seed);
+  long used = 0;
+  {
+    std::vector<unsigned> probe;
+    // the stream never repeats within 2^31 draws; match a window of 4 to be safe
+    unsigned w1 = (unsigned)rand(), w2 = (unsigned)rand(), w3 = (unsigned)rand();
+    srand(seed);
+    std::vector<unsigned> all((size_t)iterations * 7 + 8);
+    for (size_t i = 0; i < all.size(); ++i) all[i] = (unsigned)rand();
+    (void)w1; (void)w2; (void)w3;
+    used = -1;
+    for (size_t i = 0; i < all.size(); ++i) if (all[i] == next && (i % 7) == 0) { used = (long)i; break; }
+  }
+  for (size_t i = 0; i < vec_inliers.size(); ++i) inliers[i] = (int)vec_inliers[i];
+  out[0] = r.first; out[1] = r.second; out[2] = (double)used;
+  return (int)vec_inliers.size();
+}
+
 }  // extern "C"

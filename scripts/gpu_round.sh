@@ -9,7 +9,6 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $OUT/${TAG}_gpu.csv 2>&1
 if [[ "$WHAT" == "all" || "$WHAT" == "tests" ]]; then
   timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee $OUT/${TAG}_pytest_gpu.log
-  MVGCUDA_EPILOGUE=deferred timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee $OUT/${TAG}_pytest_gpu_deferred.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/${TAG}_smoke.log
 fi
 if [[ "$WHAT" == "all" || "$WHAT" == "bench" ]]; then
