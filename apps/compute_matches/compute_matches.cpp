@@ -22,8 +22,12 @@
 //   3. the i < j pair list is cut into contiguous, cost-balanced (rows_i * rows_j) shards, one per GPU; every GPU runs
 //      rows 7-13 of the path on its shard (mvgcuda_match_collection; batches pipelined inside the library);
 //   4. the text of every shard is formatted concurrently and written in pair order.
-// Out of scope of this build: SIFT extraction (the stage before: .feat/.desc must exist) and
-// the AC-RANSAC geometric filter (the stage after: run the reference's own binary on the exported file).
+//   5. -g f: the AC-RANSAC fundamental-matrix filter (compute_matches.cpp:250-318, GeometricFilter_FMatrix_AC(4.0)) runs
+//      on GPU 0 over the putative matches (fresh or imported) and writes <outdir>/matches.f.txt; the reference's rand()
+//      stream is never seeded (== srand(1)) and is consumed pair after pair in map order -- reproduced.
+// Out of scope of this build: SIFT extraction (the stage before: .feat/.desc must exist) and the
+// essential / homography variants of the filter (-g e, the reference's default, needs K.txt; -g h): they stop after the
+// putative stage with a message.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -90,14 +94,27 @@ std::string basename_part(const std::string& f) {  // file_system.h basename_par
   return d == std::string::npos ? b : b.substr(0, d);
 }
 
-bool load_list(const std::string& path, std::vector<std::string>& names) {
+// lists.txt: "name;width;height[;focal;...]" (image_list_io_helper.h:69-193); sizes gets width, height per image (0 when absent)
+bool load_list(const std::string& path, std::vector<std::string>& names, std::vector<int32_t>& sizes) {
   std::ifstream in(path.c_str());
   if (!in.is_open()) return false;
   std::string line;
   while (std::getline(in, line)) {
     while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
     if (line.empty()) continue;
-    names.push_back(line.substr(0, line.find(';')));
+    std::vector<std::string> f;
+    size_t b = 0;
+    for (;;) {
+      const size_t e = line.find(';', b);
+      f.push_back(line.substr(b, e == std::string::npos ? std::string::npos : e - b));
+      if (e == std::string::npos) break;
+      b = e + 1;
+    }
+    names.push_back(f[0]);
+    int w = 0, h = 0;
+    if (f.size() >= 3) { w = atoi(f[1].c_str()); h = atoi(f[2].c_str()); }
+    sizes.push_back(w);
+    sizes.push_back(h);
   }
   return true;
 }
@@ -218,17 +235,23 @@ int main(int argc, char** argv) {
   if (!dir_exists(opt.outdir)) { std::cerr << "output directory " << opt.outdir << " does not exist" << std::endl; return EXIT_FAILURE; }
 
   std::vector<std::string> names;
-  if (!load_list(opt.outdir + "/lists.txt", names)) {
+  std::vector<int32_t> image_sizes;
+  if (!load_list(opt.outdir + "/lists.txt", names, image_sizes)) {
     std::cerr << "\nEmpty or invalid image list: " << opt.outdir << "/lists.txt" << std::endl;
     return EXIT_FAILURE;
   }
   const std::string putative = opt.outdir + "/matches.putative.txt";
-  if (file_exists(putative)) {  // compute_matches.cpp:230-234
-    ImportedMatches im;
+  const bool filter_f = opt.geometric_model == "f";
+  const bool resumed = file_exists(putative);
+  ImportedMatches im;
+  if (resumed) {  // compute_matches.cpp:230-234
     if (!import_matches(putative, im)) return EXIT_FAILURE;
     std::cout << std::endl << "PUTATIVE MATCHES -- PREVIOUS RESULTS LOADED" << std::endl
               << im.pairs << " pairs, " << im.matches << " putative matches imported from " << putative << "; matching skipped" << std::endl;
-    return EXIT_SUCCESS;
+    if (!filter_f) {
+      std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f is)" << std::endl;
+      return EXIT_SUCCESS;
+    }
   }
 
   typedef std::chrono::steady_clock Clock;
@@ -254,6 +277,7 @@ int main(int argc, char** argv) {
   if (n_devices < 1) { std::cerr << "no sm_100 CUDA device visible (there is no CPU fallback)" << std::endl; return EXIT_FAILURE; }
   int gpus = opt.gpus > 0 ? opt.gpus : n_devices;  // more shards than devices: they share devices round-robin
   gpus = (int)std::max<int64_t>(1, std::min<int64_t>(gpus, std::max<int64_t>(n_pairs, 1)));
+  if (resumed) gpus = 1;  // only the filter runs, and the chain of its rand() stream is walked by one GPU
   std::vector<mvgcuda_ctx*> ctxs(gpus, (mvgcuda_ctx*)NULL);
   std::vector<std::string> ctx_error(gpus);
   auto destroy_all = [&]() { for (mvgcuda_ctx* c : ctxs) if (c) mvgcuda_destroy(c); };
@@ -348,6 +372,13 @@ int main(int argc, char** argv) {
   free_staging();
   const Clock::time_point t_load = Clock::now();
 
+  // putative matches of the whole collection for the filter: pairs in std::map order, counts, offsets, (_i, _j)
+  std::vector<int32_t> put_pairs, put_counts, put_matches;
+  std::vector<int64_t> put_offsets;
+  Clock::time_point t_match = t_load, t_export = t_load;
+  long long total = 0;
+  float gpu_ms_max = 0;
+  if (!resumed) {
   // ---- 3. pair shards
   std::vector<int32_t> pairs;
   pairs.reserve((size_t)n_pairs * 2);
@@ -374,6 +405,10 @@ int main(int argc, char** argv) {
       return;
     }
     S.gpu_ms = pm.gpu_ms;
+    if (filter_f) {  // the filter needs the lists themselves (the library's buffers are reused by the next call)
+      S.counts.assign(pm.counts, pm.counts + (e - b));
+      S.matches.assign(pm.matches, pm.matches + 2 * pm.offsets[e - b]);
+    }
     // the text of the shard, straight from the library's result buffers (pairs are in lexicographic (i, j) order ==
     // std::map iteration order)
     std::string& out = S.text;
@@ -396,28 +431,81 @@ int main(int argc, char** argv) {
     for (int g = 0; g < gpus; ++g) th.emplace_back(work, g);
     for (auto& t : th) t.join();
   }
-  const Clock::time_point t_match = Clock::now();
+  t_match = Clock::now();
   for (int g = 0; g < gpus; ++g)
     if (!shards[g].error.empty()) { std::cerr << "GPU " << g << ": " << shards[g].error << std::endl; destroy_all(); return EXIT_FAILURE; }
 
   // ---- 4. export in shard (== pair) order
   FILE* f = fopen(putative.c_str(), "wb");
   if (!f) { std::cerr << "cannot write " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
-  long long total = 0;
   bool ok = true;
   for (int g = 0; g < gpus; ++g) {
     ok = ok && fwrite(shards[g].text.data(), 1, shards[g].text.size(), f) == shards[g].text.size();
     total += shards[g].total;
   }
   if (fclose(f) != 0 || !ok) { std::cerr << "short write to " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
-  const Clock::time_point t_export = Clock::now();
-  destroy_all();
-  float gpu_ms_max = 0;
+  t_export = Clock::now();
   for (int g = 0; g < gpus; ++g) gpu_ms_max = std::max(gpu_ms_max, shards[g].gpu_ms);
-  std::cout << "start-up (contexts + headers) " << ms(t_begin, t_ctx) << " ms; load (parse + upload to " << gpus << " GPU(s)) " << ms(t_ctx, t_load)
-            << " ms; match + format " << ms(t_load, t_match) << " ms (GPU time " << gpu_ms_max << " ms, " << n_pairs << " pairs, " << total
-            << " putative matches, " << (n_pairs / std::max(1e-9, ms(t_load, t_match) * 1e-3)) << " pairs/s); export " << ms(t_match, t_export)
-            << " ms -> " << putative << std::endl;
-  std::cout << "geometric filtering (-g " << opt.geometric_model << ") is the next stage and is not part of this build" << std::endl;
+  if (filter_f) {
+    put_pairs = pairs;
+    put_counts.reserve((size_t)n_pairs);
+    put_matches.reserve((size_t)total * 2);
+    for (int g = 0; g < gpus; ++g) {
+      put_counts.insert(put_counts.end(), shards[g].counts.begin(), shards[g].counts.end());
+      put_matches.insert(put_matches.end(), shards[g].matches.begin(), shards[g].matches.end());
+    }
+  }
+  } else {
+    // imported putatives with the map semantics of pairedIndexedMatchImport: distinct keys in order, the LAST block of a key wins
+    std::vector<size_t> order(im.blocks.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return im.blocks[x].first < im.blocks[y].first; });
+    for (size_t k = 0; k < order.size(); ++k) {
+      if (k + 1 < order.size() && im.blocks[order[k + 1]].first == im.blocks[order[k]].first) continue;
+      const auto& blk = im.blocks[order[k]];
+      if (blk.first.first >= (size_t)n || blk.first.second >= (size_t)n) { std::cerr << "imported pair out of range" << std::endl; destroy_all(); return EXIT_FAILURE; }
+      put_pairs.push_back((int32_t)blk.first.first);
+      put_pairs.push_back((int32_t)blk.first.second);
+      put_counts.push_back((int32_t)blk.second.size());
+      for (const auto& m : blk.second) { put_matches.push_back(m.first); put_matches.push_back(m.second); }
+    }
+  }
+  if (!resumed)
+    std::cout << "start-up (contexts + headers) " << ms(t_begin, t_ctx) << " ms; load (parse + upload to " << gpus << " GPU(s)) " << ms(t_ctx, t_load)
+              << " ms; match + format " << ms(t_load, t_match) << " ms (GPU time " << gpu_ms_max << " ms, " << n_pairs << " pairs, " << total
+              << " putative matches, " << (n_pairs / std::max(1e-9, ms(t_load, t_match) * 1e-3)) << " pairs/s); export " << ms(t_match, t_export)
+              << " ms -> " << putative << std::endl;
+  if (!filter_f) {
+    destroy_all();
+    std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f is)" << std::endl;
+    return EXIT_SUCCESS;
+  }
+  // ---- 5. geometric filter (fundamental matrix, AC-RANSAC) on GPU 0
+  std::cout << std::endl << " - GEOMETRIC FILTERING - " << std::endl;
+  const size_t np = put_counts.size();
+  put_offsets.assign(np + 1, 0);
+  for (size_t k = 0; k < np; ++k) put_offsets[k + 1] = put_offsets[k] + put_counts[k];
+  if (put_matches.empty()) put_matches.assign(2, 0);
+  mvgcuda_pair_matches gm;
+  const double max_residual_error = 4.0;  // compute_matches.cpp:254
+  if (mvgcuda_geometric_filter(ctxs[0], 'f', max_residual_error, 4096, 1u, (int64_t)np, put_pairs.data(), put_counts.data(), put_offsets.data(),
+                               put_matches.data(), image_sizes.data(), &gm) != MVGCUDA_OK) {
+    std::cerr << "geometric filter: " << mvgcuda_last_error(ctxs[0]) << std::endl;
+    destroy_all();
+    return EXIT_FAILURE;
+  }
+  const Clock::time_point t_geo = Clock::now();
+  const std::string geo_path = opt.outdir + "/matches.f.txt";  // compute_matches.cpp:64-66,131-133
+  if (mvgcuda_write_matches(geo_path.c_str(), gm.n_pairs, put_pairs.data(), gm.counts, gm.offsets, gm.matches, 1) != MVGCUDA_OK) {
+    std::cerr << "cannot write " << geo_path << std::endl;
+    destroy_all();
+    return EXIT_FAILURE;
+  }
+  long long kept_pairs = 0;
+  for (int64_t k = 0; k < gm.n_pairs; ++k) kept_pairs += gm.counts[k] > 0;
+  std::cout << "geometric filter (F, AC-RANSAC, 4096 iterations, " << max_residual_error << " px) " << ms(t_export, t_geo) << " ms (GPU time " << gm.gpu_ms << " ms): "
+            << kept_pairs << " of " << np << " pairs kept, " << gm.offsets[gm.n_pairs] << " matches, " << gm.rescanned_queries
+            << " rand() values consumed, " << gm.knn_kernel_launches << " models re-evaluated with host roots -> " << geo_path << std::endl;
+  destroy_all();
   return EXIT_SUCCESS;
 }

@@ -41,3 +41,21 @@ def test_adaptors_against_reference_classes(pkg, et, tmp_path):
     names = _write_et(pkg, et, tmp_path, 8)
     out = subprocess.run([ADAPT, str(tmp_path), *names], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ADAPTORS OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_compute_matches_geometric_stage_golden(pkg, et, tmp_path):
+    """`compute_matches -r 0.6 -g f` == the reference's two stages on data/et: matches.putative.txt and matches.f.txt
+    (GeometricFilter_FMatrix_AC(4.0), never-seeded rand()) byte for byte; a second run imports the putatives
+    (pairedIndexedMatchImport) and filters again -- same file."""
+    _write_et(pkg, et, tmp_path, 4)
+    want_f = open(os.path.join(GOLDEN, "et_matches_f.txt"), "rb").read()
+    for second in (False, True):
+        out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "f", "--gpus", "1"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr + out.stdout
+        assert ("PREVIOUS RESULTS LOADED" in out.stdout) == second
+        assert (tmp_path / "matches.putative.txt").read_bytes() == open(os.path.join(GOLDEN, "et_putative_r0.6.txt"), "rb").read()
+        assert (tmp_path / "matches.f.txt").read_bytes() == want_f
+        os.remove(tmp_path / "matches.f.txt")
+    # the other models stop after the putative stage
+    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "h"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "only -g f" in out.stdout and not (tmp_path / "matches.f.txt").exists()

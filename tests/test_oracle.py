@@ -307,3 +307,29 @@ def test_match_file_import_mirrors_reference_reader(tmp_path, l0):
     # the reference pads the short block with default IndexedMatch (0, 0) entries; the mirror must agree on every complete block
     assert got.split("7 8\n3\n")[0] == want.split("7 8\n3\n")[0]
     assert "0 1\n2\n5 6\n7 8\n" in got
+
+
+def _native(name, tmp_path):
+    """Compile tests/native/<name>.cpp against oracle/_ref/libmvgref_geom.so and run it."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "libmvgref_geom.so")):
+        pytest.skip("geometric-filter oracle (oracle/_ref/libmvgref_geom.so) not built here")
+    exe = os.path.join(tmp_path, name)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "native", name + ".cpp"),
+                           "-L" + ref, "-lmvgref_geom", "-Wl,-rpath," + ref])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_acransac_core_bit_exact_vs_reference(tmp_path):
+    """csrc/acransac_core.cuh compiled for the host: glibc rand(), RandomSample, NormalizePoints, the 7-point solver
+    (Eigen 3.2.2 JacobiSVD restated) and the residual, bit for bit against the reference's own classes."""
+    assert "ACRANSAC CORE OK" in _native("test_acransac_core", tmp_path)
+
+
+def test_acransac_engine_vs_reference(tmp_path):
+    """csrc/acransac_engine.cuh (ranges of iterations evaluated speculatively, accounted for in order) against the
+    reference's sequential ACRANSAC: inliers in order, minNFA / errorMax bits, rand() consumption."""
+    assert "ACRANSAC ENGINE OK" in _native("test_acransac_engine", tmp_path)
