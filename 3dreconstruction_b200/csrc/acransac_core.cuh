@@ -249,6 +249,18 @@ MVG_GEO_HD int solve_cubic(const double* P /* ascending powers */, double* roots
 
 // ------------------------------------------------------------------------------------------ 7-point solver
 // x1, x2: the 7 sampled (normalised) correspondences, [7][2].  W, V: 81 doubles of scratch each.
+// det(F1 + a F2) as a cubic in a, ascending powers (solver_fundamental_kernel.cpp:37-59; F1 = Map<RMat3>(f1): F1(r, c) = f1[3 r + c]).
+MVG_GEO_HD void cubic_from_null_vectors(const double* f1, const double* f2, double* P) {
+  const double a = f1[0], j = f2[0], b = f1[1], k = f2[1], c = f1[2], l = f2[2], d = f1[3], m = f2[3], e = f1[4], n = f2[4],
+               f = f1[5], o = f2[5], g = f1[6], p = f2[6], h = f1[7], q = f2[7], i = f1[8], r = f2[8];
+  P[0] = a * e * i + b * f * g + c * d * h - a * f * h - b * d * i - c * e * g;
+  P[1] = a * e * r + a * i * n + b * f * p + b * g * o + c * d * q + c * h * m + d * h * l + e * i * j + f * g * k -
+         a * f * q - a * h * o - b * d * r - b * i * m - c * e * p - c * g * n - d * i * k - e * g * l - f * h * j;
+  P[2] = a * n * r + b * o * p + c * m * q + d * l * q + e * j * r + f * k * p + g * k * o + h * l * m + i * j * n -
+         a * o * q - b * m * r - c * n * p - d * k * r - e * l * p - f * j * q - g * l * n - h * j * o - i * k * m;
+  P[3] = j * n * r + k * o * p + l * m * q - j * o * q - k * m * r - l * n * p;
+}
+
 // Step 1 (pure IEEE arithmetic, bit-identical on every machine): the two null vectors f1 = V.col(8), f2 = V.col(7)
 // (numeric.h:252-253) and the coefficients P of det(F1 + a F2), ascending powers.
 MVG_GEO_HD void seven_point_basis(const double* x1, const double* x2, double* W, double* V, double* P) {
@@ -260,16 +272,7 @@ MVG_GEO_HD void seven_point_basis(const double* x1, const double* x2, double* W,
     W[i + 9 * 6] = u1;      W[i + 9 * 7] = v1;      W[i + 9 * 8] = 1.0;
   }
   jacobi_svd9_v(W, V);
-  const double* f1 = V + 9 * 8;  // F1 = Map<RMat3>(f1): F1(r, c) = f1[3 r + c]
-  const double* f2 = V + 9 * 7;
-  const double a = f1[0], j = f2[0], b = f1[1], k = f2[1], c = f1[2], l = f2[2], d = f1[3], m = f2[3], e = f1[4], n = f2[4],
-               f = f1[5], o = f2[5], g = f1[6], p = f2[6], h = f1[7], q = f2[7], i = f1[8], r = f2[8];
-  P[0] = a * e * i + b * f * g + c * d * h - a * f * h - b * d * i - c * e * g;
-  P[1] = a * e * r + a * i * n + b * f * p + b * g * o + c * d * q + c * h * m + d * h * l + e * i * j + f * g * k -
-         a * f * q - a * h * o - b * d * r - b * i * m - c * e * p - c * g * n - d * i * k - e * g * l - f * h * j;
-  P[2] = a * n * r + b * o * p + c * m * q + d * l * q + e * j * r + f * k * p + g * k * o + h * l * m + i * j * n -
-         a * o * q - b * m * r - c * n * p - d * k * r - e * l * p - f * j * q - g * l * n - h * j * o - i * k * m;
-  P[3] = j * n * r + k * o * p + l * m * q - j * o * q - k * m * r - l * n * p;
+  cubic_from_null_vectors(V + 9 * 8, V + 9 * 7, P);
 }
 // Step 2: the models F1 + root * F2 (solver_fundamental_kernel.cpp:62-64); F(r, c) at [3 r + c].
 MVG_GEO_HD void models_from_roots(const double* f1, const double* f2, const double* roots, int nr, double* F) {

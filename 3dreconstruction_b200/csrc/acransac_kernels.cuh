@@ -185,6 +185,67 @@ __device__ __forceinline__ void best_nfa_warp(const GeoBatchDev& B, const GeoPai
   k_best = v < ac_inf() ? kb : kSampleF;
 }
 
+// jacobi_svd9_v (acransac_core.cuh) with the warp cooperating: the 2x2 step is computed by every lane (same inputs from
+// shared memory, same bits), lanes 0-8 then rotate one element pair of the two rows / columns of W each and lanes 9-17 one
+// element pair of V's columns.  Per element exactly the scalar version's operations, so V is bit-identical to it.
+__device__ __forceinline__ void jacobi_svd9_v_warp(double* W, double* V, int lane) {
+  const double precision = 2.0 * DBL_EPSILON;
+  const double consider_as_zero = 2.0 * 4.9406564584124654e-324;
+  for (int i = lane; i < 81; i += 32) V[i] = (i % 10 == 0) ? 1.0 : 0.0;
+  double scale = 0.0;
+  for (int i = lane; i < 81; i += 32) { const double a = fabs(W[i]); if (a > scale) scale = a; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, scale, o); if (t > scale) scale = t; }
+  if (scale == 0.0) scale = 1.0;
+  const double inv = 1.0 / scale;
+  __syncwarp();
+  for (int i = lane; i < 81; i += 32) W[i] *= inv;
+  __syncwarp();
+  bool finished = false;
+  while (!finished) {
+    finished = true;
+    for (int p = 1; p < 9; ++p) {
+      for (int q = 0; q < p; ++q) {
+        const double wpp = W[p + 9 * p], wqq = W[q + 9 * q], wpq = W[p + 9 * q], wqp = W[q + 9 * p];
+        const double app = fabs(wpp), aqq = fabs(wqq);
+        const double mx = app < aqq ? aqq : app;
+        const double pm = precision * mx;
+        const double threshold = consider_as_zero < pm ? pm : consider_as_zero;
+        const double apq = fabs(wpq), aqp = fabs(wqp);
+        const double off = apq < aqp ? aqp : apq;
+        if (off > threshold) {  // warp-uniform: every lane read the same four values
+          finished = false;
+          Rot jl, jr;
+          real_2x2_jacobi_svd(wpp, wpq, wqp, wqq, jl, jr);
+          __syncwarp();
+          if (lane < 9 && !(jl.c == 1.0 && jl.s == 0.0)) rotate_pair(W[p + 9 * lane], W[q + 9 * lane], jl.c, jl.s);
+          __syncwarp();
+          if (!(jr.c == 1.0 && -jr.s == 0.0)) {
+            if (lane < 9) rotate_pair(W[lane + 9 * p], W[lane + 9 * q], jr.c, -jr.s);
+            else if (lane < 18) rotate_pair(V[(lane - 9) + 9 * p], V[(lane - 9) + 9 * q], jr.c, -jr.s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // singular values = |diagonal|, selection sort in descending order (first maximum wins), stop at an exact zero
+  double sv[9];
+  for (int i = 0; i < 9; ++i) sv[i] = fabs(W[i + 9 * i]);
+  for (int i = 0; i < 9; ++i) {
+    int pos = 0;
+    double best = sv[i];
+    for (int k = 1; k < 9 - i; ++k) if (sv[i + k] > best) { best = sv[i + k]; pos = k; }
+    if (best == 0.0) break;
+    if (pos) {
+      pos += i;
+      const double t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
+      if (lane < 9) { const double u = V[lane + 9 * pos]; V[lane + 9 * pos] = V[lane + 9 * i]; V[lane + 9 * i] = u; }
+    }
+  }
+  __syncwarp();
+}
+
 // All models of one iteration (already in ws.F): best NFA over the models, strict <, in order (estimator_acransac.h:173-217).
 __device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, const GeoPairDev& P, WarpScratch& ws, int nm, double* ge, int* gi, int lane) {
   double best = ac_inf();
@@ -228,14 +289,20 @@ geo_eval_kernel(GeoBatchDev B) {
     for (int k = 0; k < kSampleF; ++k) r[k] = r7[k];
     int s[kSampleF];
     random_sample<kSampleF>(r, R.n_index, s);
-    double a[2 * kSampleF], b[2 * kSampleF];
-    for (int k = 0; k < kSampleF; ++k) {
+    for (int i = 0; i < 81; ++i) ws.W[i] = 0.0;
+    for (int k = 0; k < kSampleF; ++k) {  // EncodeEpipolarEquation (seven_point_basis)
       const int id = identity ? s[k] : B.vec_index[s[k]];
       const double2 p = B.x1[P.m_off + id], q = B.x2[P.m_off + id];
-      a[2 * k] = p.x; a[2 * k + 1] = p.y; b[2 * k] = q.x; b[2 * k + 1] = q.y;
+      ws.W[k + 9 * 0] = q.x * p.x; ws.W[k + 9 * 1] = q.x * p.y; ws.W[k + 9 * 2] = q.x;
+      ws.W[k + 9 * 3] = q.y * p.x; ws.W[k + 9 * 4] = q.y * p.y; ws.W[k + 9 * 5] = q.y;
+      ws.W[k + 9 * 6] = p.x;       ws.W[k + 9 * 7] = p.y;       ws.W[k + 9 * 8] = 1.0;
     }
+  }
+  __syncwarp();
+  jacobi_svd9_v_warp(ws.W, ws.V, lane);
+  if (lane == 0) {
     double Pc[4], roots[3];
-    seven_point_basis(a, b, ws.W, ws.V, Pc);
+    cubic_from_null_vectors(ws.V + 9 * 8, ws.V + 9 * 7, Pc);
     const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
     models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
     ws.n_models = nr;

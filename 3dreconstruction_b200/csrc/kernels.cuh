@@ -614,9 +614,11 @@ tie_fixup_kernel(const uint8_t* __restrict__ arena, const uint8_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ K3
-constexpr int kCompactThreads = 256;
+// 128 threads x <= 40 registers and ~1 KB of shared memory: a CTA of these kernels fits NEXT TO a resident knn2_kernel CTA
+// (608 threads x 96 registers, 197 KB), so the compaction of batch k runs under the fused kernel of batch k + 1.
+constexpr int kCompactThreads = 128;
 
-// Exclusive block-wide rank of `flag` among the 256 threads + block total (ordered by threadIdx).
+// Exclusive block-wide rank of `flag` among the threads of the block + block total (ordered by threadIdx).
 __device__ __forceinline__ int block_rank(bool flag, int* warp_tot /*[8] smem*/, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned m = __ballot_sync(0xffffffffu, flag);
@@ -741,16 +743,18 @@ ratio_filter_kernel(const PairJob* __restrict__ jobs, const KnnRecord* __restric
   if (threadIdx.x == 0) { n_pass[blockIdx.x] = base_out; counts[blockIdx.x] = kept; }
 }
 
-// Exclusive scan of counts over the batch (single CTA; batches are a few thousand pairs).
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ counts, int n,
-                                                           long long base, long long* __restrict__ offsets,
-                                                           long long* __restrict__ total_out) {
-  __shared__ long long warp_sum[32];
+// Exclusive scan of counts over the batch (single CTA of kScanThreads; batches are a few thousand pairs).
+constexpr int kScanThreads = 128;
+__global__ void __launch_bounds__(kScanThreads) scan_counts_kernel(const int* __restrict__ counts, int n,
+                                                                   long long base, long long* __restrict__ offsets,
+                                                                   long long* __restrict__ total_out) {
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ long long warp_sum[kWarps];
   __shared__ long long carry_s;
   if (threadIdx.x == 0) carry_s = base;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i0 = 0; i0 < n; i0 += 1024) {
+  for (int i0 = 0; i0 < n; i0 += kScanThreads) {
     const int i = i0 + threadIdx.x;
     const long long v = i < n ? counts[i] : 0;
     long long x = v;
@@ -761,21 +765,17 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict
     }
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-      long long w = warp_sum[lane];
+    long long before = 0, tot = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;  // inclusive
+    for (int w = 0; w < kWarps; ++w) {
+      const long long c = warp_sum[w];
+      if (w < warp) before += c;
+      tot += c;
     }
-    __syncthreads();
     const long long carry = carry_s;
-    const long long excl = carry + (warp ? warp_sum[warp - 1] : 0) + (x - v);
-    if (i < n) offsets[i] = excl;
+    if (i < n) offsets[i] = carry + before + (x - v);
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_sum[31];
+    if (threadIdx.x == 0) carry_s = carry + tot;
     __syncthreads();
   }
   if (threadIdx.x == 0) { offsets[n] = carry_s; *total_out = carry_s; }
@@ -934,17 +934,19 @@ plan_rescan_kernel(const PairJob* __restrict__ jobs, const int* __restrict__ res
 // Shared-memory form: one warp per pair; lane 0 builds the tree in 16-byte nodes held in shared memory (a dependent
 // shared-memory load per level instead of an L2 round trip: ~40x less latency per insertion), the other lanes gather the keys
 // and write the survivors.  Pairs with more than `cap` matches are left to dedup_xy_kernel below.
-constexpr int kDedupSmemCap = 2047;  // 2048 nodes of 16 B + 2048 order entries of 2 B = 36 KB per CTA: 6 pairs in flight per SM
+constexpr int kDedupSmemCap = 2047;       // 2048 nodes of 16 B + 2048 order entries of 2 B = 36 KB per CTA: 6 pairs in flight per SM
+constexpr int kDedupSmemCapSmall = 1023;  // 18 KB: fits beside a resident knn2_kernel CTA (batches that have a successor)
+template <int kCap>
 __global__ void __launch_bounds__(32)
 dedup_xy_smem_kernel(const PairJob* __restrict__ jobs, const int2* __restrict__ matches, const long long* __restrict__ offsets,
                      const int* __restrict__ counts, const float2* __restrict__ feats, int2* __restrict__ out,
                      int* __restrict__ counts2) {
-  __shared__ RbNode16 nd[kDedupSmemCap + 1];
-  __shared__ unsigned short ord[kDedupSmemCap + 1];
+  __shared__ RbNode16 nd[kCap + 1];
+  __shared__ unsigned short ord[kCap + 1];
   __shared__ int kept_s;
   const int p = blockIdx.x, lane = threadIdx.x;
   const int n = counts[p];
-  if (n > kDedupSmemCap) return;
+  if (n > kCap) return;
   if (n == 0) { if (lane == 0) counts2[p] = 0; return; }
   const long long off = offsets[p];
   const int db_row0 = jobs[p].db_row0;

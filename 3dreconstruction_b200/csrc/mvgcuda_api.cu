@@ -78,7 +78,7 @@ struct BatchSlot {
   PinnedBuf<long long> h_offsets;
   PinnedBuf<RescanMeta> h_meta;
   PinnedBuf<int> h_resc_cnt;
-  cudaEvent_t ev_start = nullptr, ev_knn = nullptr, ev_done = nullptr, ev_copied = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_knn = nullptr, ev_ready = nullptr, ev_done = nullptr, ev_copied = nullptr;
   // bookkeeping of the batch currently in the slot
   int64_t p0 = 0;
   int nb = 0, n_items = 0, launches = 0;
@@ -88,7 +88,7 @@ struct BatchSlot {
     d_jobs.release(); d_item_start.release(); d_knn.release(); d_resc_idx.release(); d_resc_cnt.release(); d_meta.release();
     d_matches.release(); d_counts.release(); d_offsets.release();
     h_jobs.release(); h_item_start.release(); h_counts.release(); h_offsets.release(); h_meta.release(); h_resc_cnt.release();
-    for (cudaEvent_t* e : {&ev_start, &ev_knn, &ev_done, &ev_copied}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaEvent_t* e : {&ev_start, &ev_knn, &ev_ready, &ev_done, &ev_copied}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
   }
 };
 
@@ -107,6 +107,7 @@ struct mvgcuda_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;       // compute (own_stream, or the caller's)
   cudaStream_t copy_stream = nullptr;  // D2H of finished batches
+  cudaStream_t post_stream = nullptr;  // rows 10-13 of batch k (small CTAs) under the fused kernel of batch k + 1
   cudaStream_t upload_stream = nullptr;  // H2D of streamed images (+ their constants kernel), concurrent with matching
   char error[1024] = "";
   size_t knn_smem = 0;
@@ -490,8 +491,7 @@ static int rescan_bounded(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S) {
 // Rows 10-13 for the batch in slot S: ratio test + ordered compaction + drop-last + unique-on-_i (K3), then -- at the
 // collection level -- the coordinate de-duplication, one thread per pair, and a second compaction; finally the small
 // per-pair results start their way to the slot's pinned staging.
-static int compact_batch(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S, float ratio_sq, bool dedup_xy) {
-  cudaStream_t st = ctx->stream;
+static int compact_batch(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S, float ratio_sq, bool dedup_xy, cudaStream_t st, bool beside_knn) {
   const int nb = S.nb;
   const size_t nrec = (size_t)std::max<long long>(S.n_records, 1);
   CU_CHECK(ctx, ctx->d_tmp.reserve(nrec));
@@ -513,7 +513,7 @@ static int compact_batch(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S, float r
   }
   ratio_filter_kernel<<<nb, kCompactThreads, 0, st>>>(S.d_jobs.p, S.d_knn.p, ratio_sq, ctx->d_tmp.p, ctx->d_npass.p, counts1);
   CU_CHECK(ctx, cudaGetLastError());
-  scan_counts_kernel<<<1, 1024, 0, st>>>(counts1, nb, 0, offsets1, ctx->d_total.p);
+  scan_counts_kernel<<<1, kScanThreads, 0, st>>>(counts1, nb, 0, offsets1, ctx->d_total.p);
   CU_CHECK(ctx, cudaGetLastError());
   dedup_scatter_kernel<<<nb, kCompactThreads, 0, st>>>(S.d_jobs.p, ctx->d_tmp.p, ctx->d_npass.p, offsets1, 0, matches1);
   CU_CHECK(ctx, cudaGetLastError());
@@ -522,12 +522,15 @@ static int compact_batch(mvgcuda_ctx* ctx, const Arena& A, BatchSlot& S, float r
     CU_CHECK(ctx, ctx->d_nodes.reserve(nrec + nb + 1));
     CU_CHECK(ctx, ctx->d_order.reserve(nrec));
     // survivors of pair p land in d_tmp at the pair's old offset, then move to their final (dense) place
-    dedup_xy_smem_kernel<<<nb, 32, 0, st>>>(S.d_jobs.p, matches1, offsets1, counts1, A.feat.p, ctx->d_tmp.p, S.d_counts.p);
+    // a batch with a successor uses the small-footprint variant, which shares the SMs with the successor's fused kernel
+    const int cap = beside_knn ? kDedupSmemCapSmall : kDedupSmemCap;
+    if (beside_knn) dedup_xy_smem_kernel<kDedupSmemCapSmall><<<nb, 32, 0, st>>>(S.d_jobs.p, matches1, offsets1, counts1, A.feat.p, ctx->d_tmp.p, S.d_counts.p);
+    else dedup_xy_smem_kernel<kDedupSmemCap><<<nb, 32, 0, st>>>(S.d_jobs.p, matches1, offsets1, counts1, A.feat.p, ctx->d_tmp.p, S.d_counts.p);
     CU_CHECK(ctx, cudaGetLastError());
-    dedup_xy_kernel<<<(nb + 63) / 64, 64, 0, st>>>(S.d_jobs.p, nb, kDedupSmemCap, matches1, offsets1, counts1, A.feat.p, ctx->d_nodes.p,
+    dedup_xy_kernel<<<(nb + 63) / 64, 64, 0, st>>>(S.d_jobs.p, nb, cap, matches1, offsets1, counts1, A.feat.p, ctx->d_nodes.p,
                                                   ctx->d_order.p, ctx->d_tmp.p, S.d_counts.p);
     CU_CHECK(ctx, cudaGetLastError());
-    scan_counts_kernel<<<1, 1024, 0, st>>>(S.d_counts.p, nb, 0, S.d_offsets.p, ctx->d_total.p + 1);
+    scan_counts_kernel<<<1, kScanThreads, 0, st>>>(S.d_counts.p, nb, 0, S.d_offsets.p, ctx->d_total.p + 1);
     CU_CHECK(ctx, cudaGetLastError());
     compact_pairs_kernel<<<nb, kCompactThreads, 0, st>>>(ctx->d_tmp.p, offsets1, S.d_offsets.p, S.d_counts.p, S.d_matches.p);
     CU_CHECK(ctx, cudaGetLastError());
@@ -610,9 +613,12 @@ static int enqueue_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S, int64_t p0
       ++S.launches;
     }
   }
-  rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy);
+  // rows 10-13 on the post stream: small CTAs that run beside the NEXT batch's fused kernel instead of in front of it
+  CU_CHECK(ctx, cudaEventRecord(S.ev_ready, st));
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->post_stream, S.ev_ready, 0));
+  rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy, ctx->post_stream, p1 < R.n_pairs);
   if (rc) return rc;
-  CU_CHECK(ctx, cudaEventRecord(S.ev_done, st));
+  CU_CHECK(ctx, cudaEventRecord(S.ev_done, ctx->post_stream));
   return MVGCUDA_OK;
 }
 
@@ -626,9 +632,10 @@ static int finish_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S) {
     // more ambiguous queries than the gather buffer holds: everything else on the stream is drained, then this batch is
     // matched again through the bounded path (flagged lists and records are still in the slot)
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->post_stream));
     int rc = rescan_bounded(ctx, A, S);
     if (rc) return rc;
-    rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy);
+    rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy, ctx->stream, false);
     if (rc) return rc;
     CU_CHECK(ctx, cudaEventRecord(S.ev_done, ctx->stream));
     CU_CHECK(ctx, cudaEventSynchronize(S.ev_done));
@@ -650,8 +657,8 @@ static int finish_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S) {
     ctx->r_offsets.p[S.p0 + k] = R.match_base + S.h_offsets.p[k];
   }
   float ms = 0.f;
-  CU_CHECK(ctx, cudaEventElapsedTime(&ms, S.ev_start, S.ev_done));
-  R.gpu_ms += ms;
+  CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], S.ev_done));  // batches overlap: time since the first one started
+  R.gpu_ms = std::max(R.gpu_ms, ms);
   if (S.n_items) {
     CU_CHECK(ctx, cudaEventElapsedTime(&ms, S.ev_start, S.ev_knn));
     R.knn_ms += ms;
@@ -684,17 +691,24 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
     S.busy = false;
     for (cudaEvent_t* e : {&S.ev_start, &S.ev_knn, &S.ev_done})
       if (!*e) CU_CHECK(ctx, cudaEventCreate(e));
+    if (!S.ev_ready) CU_CHECK(ctx, cudaEventCreateWithFlags(&S.ev_ready, cudaEventDisableTiming));
     if (!S.ev_copied) CU_CHECK(ctx, cudaEventCreateWithFlags(&S.ev_copied, cudaEventDisableTiming));
   }
   int64_t p0 = 0;
   int k = 0;
+  bool streaming = false;  // a streamed upload is still in flight
+  for (size_t i = 0; i < A.ready.size() && !streaming; ++i) streaming = A.streamed[i] && !A.ready[i];
+  if (n_pairs > 0) CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   while (p0 < n_pairs) {
     // batch = as many consecutive pairs as fit the record budget
     int64_t p1 = p0;
     long long rec = 0;
+    // while images are still on the wire the first batches are small (1/16, 1/8, ... of the budget): the fused kernel
+    // starts after the first handful of images instead of after everything the first full batch touches
+    const long long budget = streaming && k < 4 ? (kBatchRecords >> (4 - k)) : kBatchRecords;
     while (p1 < n_pairs && (p1 - p0) < kBatchPairs) {
       const long long qr = A.rows[pairs[2 * p1 + 1]];
-      if (p1 > p0 && rec + qr > kBatchRecords) break;
+      if (p1 > p0 && rec + qr > budget) break;
       rec += qr;
       ++p1;
     }
@@ -871,10 +885,15 @@ int mvgcuda_create(int device, mvgcuda_ctx** out) try {
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
   ctx->knn_smem = sizeof(KnnSmem) + 1024;
+  // all of the SM's shared memory configured as shared: what knn2_kernel leaves (~30 KB) can then host the small CTAs of the
+  // post stream beside it
+  if ((e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(carveout)", e);
   if ((e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->knn_smem)) != cudaSuccess)
     return fail("cudaFuncSetAttribute(knn2_kernel)", e);
   if ((e = cudaFuncSetAttribute(i8_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -904,6 +923,7 @@ void mvgcuda_destroy(mvgcuda_ctx* ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
   delete ctx;
 }
 

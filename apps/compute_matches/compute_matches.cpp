@@ -30,6 +30,7 @@
 // putative stage with a message.
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -148,6 +149,29 @@ bool load_feat_xy(const std::string& path, std::vector<float>& xy) {
   float x, y, s, o;
   while (f >> x >> y >> s >> o) { xy.push_back(x); xy.push_back(y); }
   return !f.bad();
+}
+
+// "x y scale orientation" per feature (feature.h:117-133), parsed from a buffer that holds the whole file: the same token
+// rule as  in >> x >> y >> scale >> orientation  (whitespace-separated, stop at the first token that is not a number), an
+// order of magnitude faster than the stream extractors (std::from_chars rounds like strtof).  xy receives the first
+// `cap` (x, y); returns the number of complete features in the file.
+size_t parse_feat_buffer(const char* p, const char* end, float* xy, size_t cap) {
+  size_t got = 0;
+  for (;;) {
+    float v[4];
+    int k = 0;
+    for (; k < 4; ++k) {
+      while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t' || *p == '\f' || *p == '\v')) ++p;
+      if (p < end && *p == '+') ++p;
+      const std::from_chars_result r = std::from_chars(p, end, v[k]);
+      if (r.ec != std::errc() || r.ptr == p) break;
+      p = r.ptr;
+    }
+    if (k < 4) break;
+    if (got < cap) { xy[2 * got] = v[0]; xy[2 * got + 1] = v[1]; }
+    ++got;
+  }
+  return got;
 }
 
 // decimal text of a non-negative integer, appended to a buffer (the export is hundreds of MB of small integers)
@@ -302,20 +326,37 @@ int main(int argc, char** argv) {
       destroy_all();
       return EXIT_FAILURE;
     }
-  std::vector<void*> staging(n, (void*)NULL);  // per image: [rows][128] u8 then [rows][2] float, page-locked; freed after stream_end
+  // page-locked staging, carved out of per-thread slabs (one cudaHostAlloc per 64 MB instead of one per image); per image:
+  // [rows][128] u8 then [rows][2] float; freed after stream_end
+  std::vector<void*> staging;
+  std::mutex staging_mtx;
+  const size_t kSlabBytes = 64ull << 20;
   std::vector<std::mutex> ctx_mtx(gpus);
   std::atomic<int> next(0), first_bad(n), mismatch(0);
   std::string stream_error;
   std::mutex err_mtx;
   auto load = [&]() {
+    uint8_t* slab = NULL;
+    size_t slab_left = 0;
+    std::vector<char> text;
     for (int i = next++; i < n; i = next++) {
       const std::string base = opt.outdir + "/" + basename_part(names[i]);
       const size_t nrows = (size_t)rows[i];
       uint8_t* d = NULL;
       float* xy = NULL;
       if (nrows) {
-        if (mvgcuda_host_alloc(nrows * (MVGCUDA_DIM + 2 * sizeof(float)), &staging[i]) != MVGCUDA_OK) { first_bad = std::min(first_bad.load(), i); continue; }
-        d = static_cast<uint8_t*>(staging[i]);
+        const size_t need = (nrows * (MVGCUDA_DIM + 2 * sizeof(float)) + 255) & ~size_t(255);
+        if (need > slab_left) {
+          void* p_ = NULL;
+          const size_t bytes = std::max(need, kSlabBytes);
+          if (mvgcuda_host_alloc(bytes, &p_) != MVGCUDA_OK) { first_bad = std::min(first_bad.load(), i); continue; }
+          { std::lock_guard<std::mutex> lk(staging_mtx); staging.push_back(p_); }
+          slab = static_cast<uint8_t*>(p_);
+          slab_left = bytes;
+        }
+        d = slab;
+        slab += need;
+        slab_left -= need;
         xy = reinterpret_cast<float*>(d + nrows * MVGCUDA_DIM);
         std::ifstream f((base + ".desc").c_str(), std::ios::binary);
         f.seekg(hdr_bytes[i]);
@@ -326,13 +367,15 @@ int main(int argc, char** argv) {
       // the reference (matcher_all_in_memory.h:80) -- the streaming layout assumes it equals the .desc count
       size_t got = 0;
       {
-        std::ifstream f((base + ".feat").c_str());
-        float x, y, sc, o;
-        while (f >> x >> y >> sc >> o) {
-          if (got < nrows) { xy[2 * got] = x; xy[2 * got + 1] = y; }
-          ++got;
+        std::ifstream f((base + ".feat").c_str(), std::ios::binary | std::ios::ate);
+        if (f.is_open()) {
+          const std::streamoff size = f.tellg();
+          f.seekg(0);
+          text.resize((size_t)std::max<std::streamoff>(size, 0));
+          if (size > 0) f.read(text.data(), size);
+          if (f.bad() || (size > 0 && f.gcount() != size)) { first_bad = std::min(first_bad.load(), i); continue; }
+          got = parse_feat_buffer(text.data(), text.data() + text.size(), xy, nrows);
         }
-        if (f.bad()) { first_bad = std::min(first_bad.load(), i); continue; }
       }
       if (got != nrows) { ++mismatch; continue; }
       for (int g = 0; g < gpus; ++g) {
@@ -394,7 +437,8 @@ int main(int argc, char** argv) {
     for (int g = 1; g < gpus; ++g) bounds[g] = std::lower_bound(csum.begin(), csum.end(), csum[n_pairs] * g / gpus) - csum.begin();
     for (int g = 1; g <= gpus; ++g) bounds[g] = std::max(bounds[g], bounds[g - 1]);
   }
-  struct Shard { std::vector<int32_t> counts; std::vector<int32_t> matches; std::string error; float gpu_ms = 0; std::string text; long long total = 0; };
+  struct Shard { std::vector<int32_t> counts; std::vector<int32_t> matches; std::string error; float gpu_ms = 0; std::vector<std::string> text; long long total = 0; };
+  const int fmt_threads = (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)gpus);  // per shard
   std::vector<Shard> shards(gpus);
   auto work = [&](int g) {
     Shard& S = shards[g];
@@ -410,21 +454,39 @@ int main(int argc, char** argv) {
       S.matches.assign(pm.matches, pm.matches + 2 * pm.offsets[e - b]);
     }
     // the text of the shard, straight from the library's result buffers (pairs are in lexicographic (i, j) order ==
-    // std::map iteration order)
-    std::string& out = S.text;
-    out.reserve((size_t)pm.offsets[e - b] * 12 + (size_t)(e - b) * 16 + 64);
-    for (int64_t p = b; p < e; ++p) {
-      const int c = pm.counts[p - b];
-      const int32_t* m = pm.matches + 2 * pm.offsets[p - b];
-      append_uint(out, (unsigned)pairs[2 * p]); out.push_back(' ');
-      append_uint(out, (unsigned)pairs[2 * p + 1]); out.push_back('\n');
-      append_uint(out, (unsigned)c); out.push_back('\n');
-      for (int k = 0; k < c; ++k) {
-        append_uint(out, (unsigned)m[2 * k]); out.push_back(' ');
-        append_uint(out, (unsigned)m[2 * k + 1]); out.push_back('\n');
-      }
-      S.total += c;
+    // std::map iteration order), formatted by fmt_threads threads over chunks of equal match count
+    const int64_t np_ = e - b;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(fmt_threads, np_));
+    S.text.assign(nt, std::string());
+    std::vector<int64_t> cut(nt + 1, np_);
+    cut[0] = 0;
+    for (int t = 1; t < nt; ++t) {
+      const long long target = pm.offsets[np_] * t / nt;
+      cut[t] = std::lower_bound(pm.offsets, pm.offsets + np_, target) - pm.offsets;
     }
+    auto fmt = [&](int t) {
+      std::string& out = S.text[t];
+      const int64_t p0 = b + cut[t], p1 = b + cut[t + 1];
+      out.reserve((size_t)(pm.offsets[p1 - b] - pm.offsets[p0 - b]) * 12 + (size_t)(p1 - p0) * 16 + 64);
+      for (int64_t p = p0; p < p1; ++p) {
+        const int c = pm.counts[p - b];
+        const int32_t* m = pm.matches + 2 * pm.offsets[p - b];
+        append_uint(out, (unsigned)pairs[2 * p]); out.push_back(' ');
+        append_uint(out, (unsigned)pairs[2 * p + 1]); out.push_back('\n');
+        append_uint(out, (unsigned)c); out.push_back('\n');
+        for (int k = 0; k < c; ++k) {
+          append_uint(out, (unsigned)m[2 * k]); out.push_back(' ');
+          append_uint(out, (unsigned)m[2 * k + 1]); out.push_back('\n');
+        }
+      }
+    };
+    {
+      std::vector<std::thread> ft;
+      for (int t = 1; t < nt; ++t) ft.emplace_back(fmt, t);
+      fmt(0);
+      for (auto& t : ft) t.join();
+    }
+    S.total = pm.offsets[np_];
   };
   {
     std::vector<std::thread> th;
@@ -440,7 +502,7 @@ int main(int argc, char** argv) {
   if (!f) { std::cerr << "cannot write " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
   bool ok = true;
   for (int g = 0; g < gpus; ++g) {
-    ok = ok && fwrite(shards[g].text.data(), 1, shards[g].text.size(), f) == shards[g].text.size();
+    for (const std::string& chunk : shards[g].text) ok = ok && fwrite(chunk.data(), 1, chunk.size(), f) == chunk.size();
     total += shards[g].total;
   }
   if (fclose(f) != 0 || !ok) { std::cerr << "short write to " << putative << std::endl; destroy_all(); return EXIT_FAILURE; }
