@@ -42,17 +42,38 @@ struct IterRes { double nfa; int n_inl; int model; };
 constexpr int kBasisDoubles = 22;  // per iteration: f1[9], f2[9] (null vectors), P[4] (cubic, ascending powers)
 constexpr double kGuardAbs = 1e-3, kGuardRel = 1e-6;  // NFA band around a decision threshold that forces exact roots
 
-struct RoundInfo {   // what every warp needs to evaluate the current range; written by the sequencer between two barriers
+struct RoundInfo {   // what a warp needs to evaluate the current range of a slot; written by the accounting warp
   int pair, lo, hi, n_index;
   long long offset;  // absolute rand() position of iteration 0 of the pair
-  int done_all, pad;
 };
 
-struct DecideOut {   // what the host reads after geo_decide_kernel
-  int status;        // 0: evaluate `next` (same or next pair), 1: iteration `it` needs exact roots (P), 2: batch finished
+struct DecideOut {   // what the host reads after geo_decide_kernel, per slot
+  int status;        // 0: evaluate `next`, 1: iteration `it` needs exact roots (P), 2: the pair is finished
   int it;
+  int iters_final;   // >= 0 once the number of iterations the pair will run is known (the next pair's rand() offset follows)
+  int pad;
   double P[4];
   RoundInfo next;
+};
+
+// Several pairs are in flight at once, each in its own SLOT (state + per-iteration scratch): the chain only orders the
+// STARTS of the pairs -- a pair's rand() offset is known as soon as its predecessor's iteration count is final, which is
+// after the predecessor's first accepted model -- so the later rounds of a pair run beside the first rounds of the next.
+constexpr int kGeoSlots = 16;
+
+struct EvalList {    // one wave of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1])
+  int n;
+  int slot[kGeoSlots];
+  int first_warp[kGeoSlots + 1];
+};
+struct ExactList {   // iterations to re-evaluate with the host's roots
+  int n;
+  int slot[kGeoSlots], it[kGeoSlots], nr[kGeoSlots];
+  double roots[kGeoSlots][3];
+};
+struct DecideList {
+  int n;
+  int slot[kGeoSlots];
 };
 
 struct GeoBatchDev {
@@ -67,23 +88,40 @@ struct GeoBatchDev {
   const uint32_t* stream;   // stream[k] = rand() value number stream_base + k of the process
   long long stream_base;
   int max_iterations;
-  IterRes* res;             // [max_iterations + 8]
-  double* models;           // [max_iterations + 8][27]
-  double* basis;            // [max_iterations + 8][kBasisDoubles]
-  int* exact;               // [max_iterations + 8]: models computed with the host's roots
-  DecideOut* decide;
-  int* vec_index;           // [n_max]
-  double* g_e;              // long candidate lists: [warps of the grid + 1][n_cap]
+  int it_stride;            // max_iterations + 8: per-slot stride of the per-iteration arrays
+  int n_max;                // per-slot stride of vec_index
+  int n_cap;                // power of two >= n_max: stride of the candidate-list scratch
+  IterRes* res;             // [slots][it_stride]
+  double* models;           // [slots][it_stride][27]
+  double* basis;            // [slots][it_stride][kBasisDoubles]
+  int* exact;               // [slots][it_stride]: models computed with the host's roots
+  int* vec_index;           // [slots][n_max]
+  AcState* state;           // [slots]
+  RoundInfo* round;         // [slots]
+  DecideOut* decide;        // [slots]
+  double* g_e;              // long candidate lists: [slots (accounting / exact warps) + warps of an evaluation wave][n_cap]
   int* g_i;
-  int n_cap;                // power of two >= n_max
   int* out_idx;             // [matches of the batch]: inlier positions (into the pair's putative list), in residual order
   int* out_count;           // [n_pairs]
   int* out_iters;           // [n_pairs]: iterations the reference would have run (7 rand() values each)
-  RoundInfo* round;
-  AcState* state;
-  unsigned* barrier;        // zeroed before the launch
-  long long* offset_io;     // in: rand() position before the batch, out: after it
 };
+
+struct SlotView {
+  IterRes* res; double* models; double* basis; int* exact; int* vec_index; AcState* state; RoundInfo* round; DecideOut* decide;
+  double* ge; int* gi;  // the slot's own candidate scratch (accounting / exact warps)
+};
+__device__ __forceinline__ SlotView slot_view(const GeoBatchDev& B, int slot) {
+  SlotView v;
+  v.res = B.res + static_cast<size_t>(slot) * B.it_stride;
+  v.models = B.models + static_cast<size_t>(slot) * B.it_stride * 27;
+  v.basis = B.basis + static_cast<size_t>(slot) * B.it_stride * kBasisDoubles;
+  v.exact = B.exact + static_cast<size_t>(slot) * B.it_stride;
+  v.vec_index = B.vec_index + static_cast<size_t>(slot) * B.n_max;
+  v.state = B.state + slot; v.round = B.round + slot; v.decide = B.decide + slot;
+  v.ge = B.g_e + static_cast<size_t>(slot) * B.n_cap;
+  v.gi = B.g_i + static_cast<size_t>(slot) * B.n_cap;
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------ prep
 // Normalised coordinates of every putative match (NormalizePoints of both images, once per pair in the reference).
@@ -267,35 +305,40 @@ __device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, co
   return r;
 }
 
-// ------------------------------------------------------------------------------------------ evaluation of a range
-// One warp per iteration of [round.lo, round.hi) with the sampling set vec_index[0 .. n_index) (estimator_acransac.h:166-218).
+// ------------------------------------------------------------------------------------------ evaluation of ranges
+// One warp per iteration of [round.lo, round.hi) of every slot in the list, with the slot's sampling set
+// vec_index[0 .. n_index) (estimator_acransac.h:166-218).
 constexpr int kEvalWarps = 8;
 __global__ void __launch_bounds__(32 * kEvalWarps)
-geo_eval_kernel(GeoBatchDev B) {
+geo_eval_kernel(GeoBatchDev B, EvalList L) {
   __shared__ WarpScratch scratch[kEvalWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kEvalWarps + warp;
-  const RoundInfo R = *B.round;
-  const int it = R.lo + gwarp;
+  int k = 0;
+  while (k + 1 < L.n && gwarp >= L.first_warp[k + 1]) ++k;
+  if (gwarp >= L.first_warp[L.n]) return;
+  const SlotView V = slot_view(B, L.slot[k]);
+  const RoundInfo R = *V.round;
+  const int it = R.lo + (gwarp - L.first_warp[k]);
   if (it >= R.hi) return;
   const GeoPairDev P = B.pairs[R.pair];
-  const bool identity = B.state->index_it < 0;
+  const bool identity = V.state->index_it < 0;
   WarpScratch& ws = scratch[warp];
-  double* ge = B.g_e + static_cast<size_t>(gwarp) * B.n_cap;
-  int* gi = B.g_i + static_cast<size_t>(gwarp) * B.n_cap;
+  double* ge = B.g_e + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
+  int* gi = B.g_i + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
   if (lane == 0) {
     const uint32_t* r7 = B.stream + (R.offset + static_cast<long long>(kSampleF) * it - B.stream_base);
     uint32_t r[kSampleF];
-    for (int k = 0; k < kSampleF; ++k) r[k] = r7[k];
+    for (int q = 0; q < kSampleF; ++q) r[q] = r7[q];
     int s[kSampleF];
     random_sample<kSampleF>(r, R.n_index, s);
     for (int i = 0; i < 81; ++i) ws.W[i] = 0.0;
-    for (int k = 0; k < kSampleF; ++k) {  // EncodeEpipolarEquation (seven_point_basis)
-      const int id = identity ? s[k] : B.vec_index[s[k]];
-      const double2 p = B.x1[P.m_off + id], q = B.x2[P.m_off + id];
-      ws.W[k + 9 * 0] = q.x * p.x; ws.W[k + 9 * 1] = q.x * p.y; ws.W[k + 9 * 2] = q.x;
-      ws.W[k + 9 * 3] = q.y * p.x; ws.W[k + 9 * 4] = q.y * p.y; ws.W[k + 9 * 5] = q.y;
-      ws.W[k + 9 * 6] = p.x;       ws.W[k + 9 * 7] = p.y;       ws.W[k + 9 * 8] = 1.0;
+    for (int q = 0; q < kSampleF; ++q) {  // EncodeEpipolarEquation (seven_point_basis)
+      const int id = identity ? s[q] : V.vec_index[s[q]];
+      const double2 a = B.x1[P.m_off + id], b = B.x2[P.m_off + id];
+      ws.W[q + 9 * 0] = b.x * a.x; ws.W[q + 9 * 1] = b.x * a.y; ws.W[q + 9 * 2] = b.x;
+      ws.W[q + 9 * 3] = b.y * a.x; ws.W[q + 9 * 4] = b.y * a.y; ws.W[q + 9 * 5] = b.y;
+      ws.W[q + 9 * 6] = a.x;       ws.W[q + 9 * 7] = a.y;       ws.W[q + 9 * 8] = 1.0;
     }
   }
   __syncwarp();
@@ -306,37 +349,39 @@ geo_eval_kernel(GeoBatchDev B) {
     const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
     models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
     ws.n_models = nr;
-    double* bs = B.basis + static_cast<size_t>(it) * kBasisDoubles;
-    for (int k = 0; k < 9; ++k) { bs[k] = ws.V[9 * 8 + k]; bs[9 + k] = ws.V[9 * 7 + k]; }
-    for (int k = 0; k < 4; ++k) bs[18 + k] = Pc[k];
-    double* out = B.models + static_cast<size_t>(it) * 27;
-    for (int k = 0; k < 9 * nr; ++k) out[k] = ws.F[k];
+    double* bs = V.basis + static_cast<size_t>(it) * kBasisDoubles;
+    for (int q = 0; q < 9; ++q) { bs[q] = ws.V[9 * 8 + q]; bs[9 + q] = ws.V[9 * 7 + q]; }
+    for (int q = 0; q < 4; ++q) bs[18 + q] = Pc[q];
+    double* out = V.models + static_cast<size_t>(it) * 27;
+    for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
   }
   __syncwarp();
   const IterRes r = evaluate_models_warp(B, P, ws, ws.n_models, ge, gi, lane);
-  if (lane == 0) { B.res[it] = r; B.exact[it] = 0; }
+  if (lane == 0) { V.res[it] = r; V.exact[it] = 0; }
 }
 
-// The same iteration again with the roots the host's C library computed for its cubic: bit-identical to the reference.
+// The same iterations again with the roots the host's C library computed for their cubics: bit-identical to the reference.
 __global__ void __launch_bounds__(32)
-geo_exact_kernel(GeoBatchDev B, int it, int nr, double r0, double r1, double r2) {
+geo_exact_kernel(GeoBatchDev B, ExactList L) {
   __shared__ WarpScratch ws;
   const int lane = threadIdx.x;
-  const GeoPairDev P = B.pairs[B.round->pair];
+  const int k = blockIdx.x;
+  const SlotView V = slot_view(B, L.slot[k]);
+  const GeoPairDev P = B.pairs[V.round->pair];
+  const int it = L.it[k], nr = L.nr[k];
   if (lane == 0) {
-    const double roots[3] = {r0, r1, r2};
-    const double* bs = B.basis + static_cast<size_t>(it) * kBasisDoubles;
-    models_from_roots(bs, bs + 9, roots, nr, ws.F);
+    const double* bs = V.basis + static_cast<size_t>(it) * kBasisDoubles;
+    models_from_roots(bs, bs + 9, L.roots[k], nr, ws.F);
     ws.n_models = nr;
-    double* out = B.models + static_cast<size_t>(it) * 27;
-    for (int k = 0; k < 9 * nr; ++k) out[k] = ws.F[k];
+    double* out = V.models + static_cast<size_t>(it) * 27;
+    for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
   }
   __syncwarp();
-  const IterRes r = evaluate_models_warp(B, P, ws, nr, B.g_e, B.g_i, lane);
-  if (lane == 0) { B.res[it] = r; B.exact[it] = 1; }
+  const IterRes r = evaluate_models_warp(B, P, ws, nr, V.ge, V.gi, lane);
+  if (lane == 0) { V.res[it] = r; V.exact[it] = 1; }
 }
 
-// The sequencer's view of the evaluated results (warp-parallel searches; every lane returns the same value).
+// The accounting warp's view of the evaluated results (warp-parallel searches; every lane returns the same value).
 struct WarpRange {
   const IterRes* res;
   int lane;
@@ -370,58 +415,53 @@ struct WarpRange {
 
 // Lowest iteration of [lo, hi) that may lie below `thr`: exact entries are compared with thr, approximate ones with
 // thr + guard.  -1 if none.
-__device__ __forceinline__ int first_candidate(const GeoBatchDev& B, int lo, int hi, double thr, double guard, int lane) {
+__device__ __forceinline__ int first_candidate(const SlotView& V, int lo, int hi, double thr, double guard, int lane) {
   int f = 0x7fffffff;
   for (int i = lo + lane; i < hi; i += 32) {
-    const double v = B.res[i].nfa;
-    if (B.exact[i] ? v < thr : v < thr + guard) { f = i; break; }
+    const double v = V.res[i].nfa;
+    if (V.exact[i] ? v < thr : v < thr + guard) { f = i; break; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
   return f == 0x7fffffff ? -1 : f;
 }
 
-// ------------------------------------------------------------------------------------------ accounting (one warp)
-// start != 0: first call of a batch -- set up pair 0.  Otherwise: the range of `round` has been evaluated; ask for exact
-// roots where a decision needs them, else account for the range (ac_account), materialise a new sampling set or the final
-// inliers, move to the next pair, and tell the host what to evaluate next.
+// ------------------------------------------------------------------------------------------ accounting (one warp per slot)
+// The range of the slot's `round` has been evaluated: ask for exact roots where a decision needs them, else account for
+// the range (ac_account), materialise a new sampling set or the final inliers, and tell the host what comes next.
 __global__ void __launch_bounds__(32)
-geo_decide_kernel(GeoBatchDev B, int start) {
+geo_decide_kernel(GeoBatchDev B, DecideList L) {
   __shared__ WarpScratch ws;
   const int lane = threadIdx.x;
+  const SlotView V = slot_view(B, L.slot[blockIdx.x]);
   DecideOut D;
-  D.status = 0; D.it = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
-  if (start) {
-    AcState S;
-    ac_init(S, B.pairs[0].n, B.max_iterations);
-    RoundInfo N;
-    N.pair = 0; N.lo = S.iter; N.hi = ac_range_end(S); N.n_index = S.n_index; N.offset = *B.offset_io; N.done_all = 0; N.pad = 0;
-    D.next = N;
-    if (lane == 0) { *B.state = S; *B.round = N; *B.decide = D; }
-    return;
-  }
-  const RoundInfo R = *B.round;
+  D.status = 0; D.it = 0; D.iters_final = -1; D.pad = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
+  const RoundInfo R = *V.round;
   const GeoPairDev P = B.pairs[R.pair];
-  AcState S = *B.state;
+  AcState S = *V.state;
   const int lo = S.iter, hi = ac_range_end(S);
   if (!S.done && lo < hi) {
     const bool ext = S.extend_to > 0;
     const double thr = ext ? ac_inf() : (S.min_nfa < 0.0 ? S.min_nfa : 0.0);
     const double guard = ext ? 0.0 : kGuardAbs + kGuardRel * fabs(thr);
     int need = -1;
-    const int t = first_candidate(B, lo, hi, thr, guard, lane);
+    bool no_trigger_in_phase_one = false;
+    const int t = first_candidate(V, lo, hi, thr, guard, lane);
     if (t >= 0) {
-      if (!B.exact[t]) need = t;
+      if (!V.exact[t]) need = t;
     } else if (!ext && S.reserve > 0) {
+      // no iteration of the whole first phase can be a trigger (none within the guard band of 0), so the loop will run
+      // iter_num + reserve iterations whichever model the fold below settles on: the next pair may start already
+      no_trigger_in_phase_one = true;
       // end of the first phase without a trigger: the best model so far becomes the sampling set -- the minimum must be exact
-      const WarpRange WR{B.res, lane};
+      const WarpRange WR{V.res, lane};
       const int a = WR.argmin_first(lo, hi);
-      const double m = B.res[a].nfa;
+      const double m = V.res[a].nfa;
       if (m < ac_inf()) {
         const double g2 = kGuardAbs + kGuardRel * fabs(m);
         int f = 0x7fffffff;
         for (int i = lo + lane; i < hi; i += 32)
-          if (!B.exact[i] && B.res[i].nfa <= m + g2) { f = i; break; }
+          if (!V.exact[i] && V.res[i].nfa <= m + g2) { f = i; break; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
         if (f != 0x7fffffff) need = f;
@@ -429,45 +469,43 @@ geo_decide_kernel(GeoBatchDev B, int start) {
     }
     if (need >= 0) {
       D.status = 1; D.it = need;
-      const double* bs = B.basis + static_cast<size_t>(need) * kBasisDoubles;
-      for (int k = 0; k < 4; ++k) D.P[k] = bs[18 + k];
+      const double* bs = V.basis + static_cast<size_t>(need) * kBasisDoubles;
+      for (int q = 0; q < 4; ++q) D.P[q] = bs[18 + q];
       D.next = R;
-      if (lane == 0) *B.decide = D;
+      if (S.reserve == 0) D.iters_final = S.iter_num;
+      else if (no_trigger_in_phase_one) D.iters_final = S.iter_num + S.reserve;
+      if (lane == 0) *V.decide = D;
       return;
     }
   }
-  const WarpRange WR{B.res, lane};
+  const WarpRange WR{V.res, lane};
   const int old_it = S.index_it, old_model = S.index_model;
   ac_account(S, WR);
-  int pair = R.pair;
-  long long offset = R.offset;
-  int done_all = 0;
   if (!S.done && (S.index_it != old_it || S.index_model != old_model)) {
     double* e;
     int* idx;
-    model_candidates_warp(B, P, B.models + static_cast<size_t>(S.index_it) * 27 + 9 * S.index_model, ws, B.g_e, B.g_i, lane, e, idx);
-    for (int k = lane; k < S.n_index; k += 32) B.vec_index[k] = idx[k];
+    model_candidates_warp(B, P, V.models + static_cast<size_t>(S.index_it) * 27 + 9 * S.index_model, ws, V.ge, V.gi, lane, e, idx);
+    for (int q = lane; q < S.n_index; q += 32) V.vec_index[q] = idx[q];
   }
   if (S.done) {
     const int n_final = ac_final_inliers(S);
     if (n_final > 0) {
       double* e;
       int* idx;
-      model_candidates_warp(B, P, B.models + static_cast<size_t>(S.best_it) * 27 + 9 * S.best_model, ws, B.g_e, B.g_i, lane, e, idx);
-      for (int k = lane; k < n_final; k += 32) B.out_idx[P.m_off + k] = idx[k];
+      model_candidates_warp(B, P, V.models + static_cast<size_t>(S.best_it) * 27 + 9 * S.best_model, ws, V.ge, V.gi, lane, e, idx);
+      for (int q = lane; q < n_final; q += 32) B.out_idx[P.m_off + q] = idx[q];
     }
     if (lane == 0) { B.out_count[R.pair] = n_final; B.out_iters[R.pair] = S.iter_num; }
-    offset += static_cast<long long>(kSampleF) * S.iter_num;
-    ++pair;
-    if (pair < B.n_pairs) ac_init(S, B.pairs[pair].n, B.max_iterations);
-    else { done_all = 1; if (lane == 0) *B.offset_io = offset; }
   }
   __syncwarp();
-  RoundInfo N;
-  N.pair = pair; N.lo = S.iter; N.hi = ac_range_end(S); N.n_index = S.n_index; N.offset = offset; N.done_all = done_all; N.pad = 0;
-  D.status = done_all ? 2 : 0;
+  RoundInfo N = R;
+  N.lo = S.iter; N.hi = ac_range_end(S); N.n_index = S.n_index;
+  D.status = S.done ? 2 : 0;
   D.next = N;
-  if (lane == 0) { *B.state = S; *B.round = N; *B.decide = D; }
+  // the loop bound is final once the reserve has been spent (or, with nothing found so far, when the extension is fixed)
+  if (S.done || S.reserve == 0) D.iters_final = S.iter_num;
+  else if (S.extend_to > 0) D.iters_final = S.extend_to;
+  if (lane == 0) { *V.state = S; *V.round = N; *V.decide = D; }
 }
 
 // Filtered matches of the batch: pair p keeps putative[out_idx[k]] for k < out_count[p], in that (residual) order

@@ -37,12 +37,14 @@ struct GeoState {
   DevBuf<AcState> d_state;
   DevBuf<DecideOut> d_decide;
   PinnedBuf<DecideOut> h_decide;
-  DevBuf<long long> d_offset, d_offsets;
+  DevBuf<long long> d_offsets;
   PinnedBuf<GeoPairDev> h_pairs;
   PinnedBuf<int2> h_matches;
   PinnedBuf<uint32_t> h_stream;
   PinnedBuf<int> h_out_count, h_out_iters;
-  PinnedBuf<long long> h_offset, h_offsets;
+  PinnedBuf<long long> h_offsets;
+  PinnedBuf<AcState> h_state;
+  PinnedBuf<RoundInfo> h_round;
   // results of the last call
   PinnedBuf<int> r_counts;
   PinnedBuf<long long> r_offsets;
@@ -61,9 +63,9 @@ void geo_free(void* p) {
   G->d_logc_pool.release(); G->d_logc_k.release(); G->d_stream.release(); G->d_res.release(); G->d_models.release(); G->d_ge.release();
   G->d_vec_index.release(); G->d_gi.release(); G->d_out_idx.release(); G->d_out_count.release(); G->d_out_iters.release();
   G->d_round.release(); G->d_state.release(); G->d_decide.release(); G->h_decide.release(); G->d_basis.release(); G->d_exact.release();
-  G->d_offset.release(); G->d_offsets.release();
+  G->d_offsets.release(); G->h_state.release(); G->h_round.release();
   G->h_pairs.release(); G->h_matches.release(); G->h_stream.release(); G->h_out_count.release(); G->h_out_iters.release();
-  G->h_offset.release(); G->h_offsets.release(); G->r_counts.release(); G->r_offsets.release(); G->r_matches.release();
+  G->h_offsets.release(); G->r_counts.release(); G->r_offsets.release(); G->r_matches.release();
   if (G->ev0) cudaEventDestroy(G->ev0);
   if (G->ev1) cudaEventDestroy(G->ev1);
   delete G;
@@ -146,26 +148,27 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_logc_pool.p, G.logc_pool.data(), G.logc_pool.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   }
 
-  // ---- scratch: one warp per iteration of a range (at most `iterations` of them) + the accounting warp
+  // ---- scratch: kGeoSlots pairs in flight, each with its per-iteration arrays; one warp per iteration of a wave
   int n_cap = 32;
   while (n_cap < n_max) n_cap <<= 1;
-  const size_t max_warps = (size_t)((iterations + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
+  const int it_stride = iterations + 8;
+  const int max_wave_warps = 2 * ((iterations + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;  // ranges evaluated in one launch
   if (!active.empty()) {
-    GEO_CHECK(ctx, G.d_res.reserve(iterations + 8));
-    GEO_CHECK(ctx, G.d_models.reserve((size_t)(iterations + 8) * 27));
-    GEO_CHECK(ctx, G.d_basis.reserve((size_t)(iterations + 8) * kBasisDoubles));
-    GEO_CHECK(ctx, G.d_exact.reserve(iterations + 8));
-    GEO_CHECK(ctx, G.d_vec_index.reserve(n_max));
-    GEO_CHECK(ctx, G.d_ge.reserve((max_warps + 1) * n_cap));
-    GEO_CHECK(ctx, G.d_gi.reserve((max_warps + 1) * n_cap));
-    GEO_CHECK(ctx, G.d_round.reserve(1));
-    GEO_CHECK(ctx, G.d_state.reserve(1));
-    GEO_CHECK(ctx, G.d_decide.reserve(1));
-    GEO_CHECK(ctx, G.h_decide.reserve(1));
-    GEO_CHECK(ctx, G.d_offset.reserve(1));
-    GEO_CHECK(ctx, G.h_offset.reserve(1));
+    GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
+    GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
+    GEO_CHECK(ctx, G.d_basis.reserve((size_t)kGeoSlots * it_stride * kBasisDoubles));
+    GEO_CHECK(ctx, G.d_exact.reserve((size_t)kGeoSlots * it_stride));
+    GEO_CHECK(ctx, G.d_vec_index.reserve((size_t)kGeoSlots * n_max));
+    GEO_CHECK(ctx, G.d_ge.reserve((size_t)(kGeoSlots + max_wave_warps) * n_cap));
+    GEO_CHECK(ctx, G.d_gi.reserve((size_t)(kGeoSlots + max_wave_warps) * n_cap));
+    GEO_CHECK(ctx, G.d_round.reserve(kGeoSlots));
+    GEO_CHECK(ctx, G.d_state.reserve(kGeoSlots));
+    GEO_CHECK(ctx, G.d_decide.reserve(kGeoSlots));
+    GEO_CHECK(ctx, G.h_decide.reserve(kGeoSlots));
+    GEO_CHECK(ctx, G.h_state.reserve(kGeoSlots));
+    GEO_CHECK(ctx, G.h_round.reserve(kGeoSlots));
   }
-  long long exact_requests = 0, rounds = 0;
+  long long exact_requests = 0, waves = 0;
 
   // ---- the process-wide rand() stream: srand(seed) here, consumed pair after pair (the reference never seeds: seed 1)
   GlibcRand gen;
@@ -242,57 +245,111 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, G.h_stream.reserve(n_stream));
     GEO_CHECK(ctx, G.d_stream.reserve(n_stream));
     memcpy(G.h_stream.p, window.data() + (size_t)(offset - win_base), n_stream * sizeof(uint32_t));
-    G.h_offset.p[0] = offset;
-
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_pairs.p, G.h_pairs.p, nb * sizeof(GeoPairDev), cudaMemcpyHostToDevice, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_matches.p, G.h_matches.p, tot * sizeof(int2), cudaMemcpyHostToDevice, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_stream.p, G.h_stream.p, n_stream * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_offset.p, G.h_offset.p, sizeof(long long), cudaMemcpyHostToDevice, st));
     GEO_CHECK(ctx, cudaEventRecord(G.ev0, st));
 
     GeoBatchDev B;
     B.pairs = G.d_pairs.p; B.n_pairs = nb; B.matches = G.d_matches.p; B.feats = V.feats; B.x1 = G.d_x1.p; B.x2 = G.d_x2.p;
     B.logc_pool = G.d_logc_pool.p; B.logc_k = G.d_logc_k.p; B.stream = G.d_stream.p; B.stream_base = offset;
-    B.max_iterations = iterations; B.res = G.d_res.p; B.models = G.d_models.p; B.vec_index = G.d_vec_index.p;
-    B.g_e = G.d_ge.p; B.g_i = G.d_gi.p; B.n_cap = n_cap; B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p;
-    B.out_iters = G.d_out_iters.p; B.round = G.d_round.p; B.state = G.d_state.p; B.offset_io = G.d_offset.p;
-    B.basis = G.d_basis.p; B.exact = G.d_exact.p; B.decide = G.d_decide.p;
+    B.max_iterations = iterations; B.it_stride = it_stride; B.n_max = n_max; B.n_cap = n_cap;
+    B.res = G.d_res.p; B.models = G.d_models.p; B.basis = G.d_basis.p; B.exact = G.d_exact.p; B.vec_index = G.d_vec_index.p;
+    B.state = G.d_state.p; B.round = G.d_round.p; B.decide = G.d_decide.p; B.g_e = G.d_ge.p; B.g_i = G.d_gi.p;
+    B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p; B.out_iters = G.d_out_iters.p;
     geo_prep_kernel<<<nb, 256, 0, st>>>(B);
     GEO_CHECK(ctx, cudaGetLastError());
-    // The chain of pairs: evaluate a range (one warp per iteration) -> account for it (one warp) -> whatever the
-    // accounting asks for: roots of one cubic from THIS machine's C library, the next range, or the next pair.
-    geo_decide_kernel<<<1, 32, 0, st>>>(B, 1);
-    GEO_CHECK(ctx, cudaGetLastError());
-    launches += 2;
-    for (;;) {
-      GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p, G.d_decide.p, sizeof(DecideOut), cudaMemcpyDeviceToHost, st));
-      GEO_CHECK(ctx, cudaStreamSynchronize(st));
-      const DecideOut D = G.h_decide.p[0];
-      if (D.status == 2) break;
-      if (D.status == 1) {
-        double roots[3] = {0.0, 0.0, 0.0};
-        const int nr = solve_cubic(D.P, roots);  // host libm: acos / cos / pow as the reference's process would call them
-        geo_exact_kernel<<<1, 32, 0, st>>>(B, D.it, nr, roots[0], roots[1], roots[2]);
-        GEO_CHECK(ctx, cudaGetLastError());
-        ++exact_requests;
-        ++launches;
-      } else {
-        const int n_it = D.next.hi - D.next.lo;
-        if (n_it > 0) {
-          geo_eval_kernel<<<(n_it + kEvalWarps - 1) / kEvalWarps, 32 * kEvalWarps, 0, st>>>(B);
-          GEO_CHECK(ctx, cudaGetLastError());
-          ++launches;
-        }
-        ++rounds;
+    ++launches;
+
+    // The wavefront.  The chain orders only the STARTS of the pairs: pair p + 1 is admitted (into a free slot) as soon as
+    // pair p's iteration count is final -- its rand() offset follows -- and from then on the two advance side by side.
+    // Every wave: range evaluations of the slots that need one (one warp per iteration), re-evaluations with roots from
+    // THIS machine's C library for the slots that asked, the accounting warp of every slot that was served, one
+    // synchronisation.
+    enum { kFree = 0, kNeedEval = 1, kNeedExact = 2 };
+    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; };
+    HostSlot slots[kGeoSlots];
+    int next_admit = 0, done_pairs = 0;
+    int chain_tail = -1;            // slot of the youngest pair in flight while its iteration count is still open
+    long long chain_offset = offset;
+    while (done_pairs < nb) {
+      // admissions
+      while (next_admit < nb && chain_tail < 0) {
+        int sl = -1;
+        for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kFree) { sl = q; break; }
+        if (sl < 0) break;
+        AcState S0;
+        ac_init(S0, G.h_pairs.p[next_admit].n, iterations);
+        RoundInfo R0;
+        R0.pair = next_admit; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = chain_offset;
+        G.h_state.p[sl] = S0;
+        G.h_round.p[sl] = R0;
+        GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, st));
+        GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, st));
+        slots[sl].state = kNeedEval; slots[sl].pair = next_admit; slots[sl].lo = R0.lo; slots[sl].hi = R0.hi;
+        chain_tail = sl;
+        ++next_admit;
       }
-      geo_decide_kernel<<<1, 32, 0, st>>>(B, 0);
+      // this wave's work lists
+      EvalList EL; EL.n = 0; EL.first_warp[0] = 0;
+      ExactList XL; XL.n = 0;
+      DecideList DL; DL.n = 0;
+      for (int q = 0; q < kGeoSlots; ++q) {
+        HostSlot& H = slots[q];
+        if (H.state == kNeedEval) {
+          const int n_it = H.hi - H.lo;
+          if (EL.first_warp[EL.n] + n_it > max_wave_warps && EL.n > 0) continue;  // next wave
+          EL.slot[EL.n] = q;
+          EL.first_warp[EL.n + 1] = EL.first_warp[EL.n] + n_it;
+          ++EL.n;
+          DL.slot[DL.n++] = q;
+        } else if (H.state == kNeedExact) {
+          XL.slot[XL.n] = q; XL.it[XL.n] = H.it;
+          XL.nr[XL.n] = solve_cubic(H.P, XL.roots[XL.n]);  // host libm: acos / cos / pow as the reference's process would call them
+          ++XL.n;
+          DL.slot[DL.n++] = q;
+          ++exact_requests;
+        }
+      }
+      if (EL.n > 0 && EL.first_warp[EL.n] > 0) {
+        geo_eval_kernel<<<(EL.first_warp[EL.n] + kEvalWarps - 1) / kEvalWarps, 32 * kEvalWarps, 0, st>>>(B, EL);
+        GEO_CHECK(ctx, cudaGetLastError());
+        ++launches;
+      }
+      if (XL.n > 0) {
+        geo_exact_kernel<<<XL.n, 32, 0, st>>>(B, XL);
+        GEO_CHECK(ctx, cudaGetLastError());
+        ++launches;
+      }
+      geo_decide_kernel<<<DL.n, 32, 0, st>>>(B, DL);
       GEO_CHECK(ctx, cudaGetLastError());
       ++launches;
+      ++waves;
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p, G.d_decide.p, kGeoSlots * sizeof(DecideOut), cudaMemcpyDeviceToHost, st));
+      GEO_CHECK(ctx, cudaStreamSynchronize(st));
+      for (int k = 0; k < DL.n; ++k) {
+        const int q = DL.slot[k];
+        HostSlot& H = slots[q];
+        const DecideOut& D = G.h_decide.p[q];
+        if (q == chain_tail && D.iters_final >= 0) {
+          chain_offset += (long long)kSampleF * D.iters_final;
+          chain_tail = -1;
+        }
+        if (D.status == 1) {
+          H.state = kNeedExact; H.it = D.it;
+          for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
+        } else if (D.status == 2) {
+          H.state = kFree; H.pair = -1;
+          ++done_pairs;
+        } else {
+          H.state = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
+        }
+      }
     }
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_count.p, G.d_out_count.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_iters.p, G.d_out_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GEO_CHECK(ctx, cudaMemcpyAsync(G.h_offset.p, G.d_offset.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaStreamSynchronize(st));
+    const long long offset_after = chain_offset;
     long long kept_total = 0;
     for (int k = 0; k < nb; ++k) { G.h_offsets.p[k] = kept_total; kept_total += G.h_out_count.p[k]; }
     G.h_offsets.p[nb] = kept_total;
@@ -318,7 +375,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         dst[2 * q] = m.x; dst[2 * q + 1] = m.y;
       }
     }
-    offset = G.h_offset.p[0];
+    offset = offset_after;
     a0 = a1;
   }
 
