@@ -613,12 +613,17 @@ static int enqueue_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S, int64_t p0
       ++S.launches;
     }
   }
-  // rows 10-13 on the post stream: small CTAs that run beside the NEXT batch's fused kernel instead of in front of it
-  CU_CHECK(ctx, cudaEventRecord(S.ev_ready, st));
-  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->post_stream, S.ev_ready, 0));
-  rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy, ctx->post_stream, p1 < R.n_pairs);
+  // Collection level: rows 10-13 on the post stream -- small CTAs that run beside the NEXT batch's fused kernel instead of
+  // in front of it (the coordinate de-dup is a serial chain per pair: 0.6 ms of an otherwise idle GPU per batch).  Pair
+  // level: the three compaction kernels take 0.1 ms and stay in line.
+  cudaStream_t ps = R.dedup_xy ? ctx->post_stream : st;
+  if (R.dedup_xy) {
+    CU_CHECK(ctx, cudaEventRecord(S.ev_ready, st));
+    CU_CHECK(ctx, cudaStreamWaitEvent(ps, S.ev_ready, 0));
+  }
+  rc = compact_batch(ctx, A, S, R.ratio_sq, R.dedup_xy, ps, R.dedup_xy && p1 < R.n_pairs);
   if (rc) return rc;
-  CU_CHECK(ctx, cudaEventRecord(S.ev_done, ctx->post_stream));
+  CU_CHECK(ctx, cudaEventRecord(S.ev_done, ps));
   return MVGCUDA_OK;
 }
 
