@@ -120,37 +120,6 @@ bool load_list(const std::string& path, std::vector<std::string>& names, std::ve
   return true;
 }
 
-bool load_desc(const std::string& path, std::vector<uint8_t>& out, int& rows) {
-  std::ifstream f(path.c_str(), std::ios::binary | std::ios::ate);
-  rows = 0;
-  out.clear();
-  if (!f.is_open()) return true;  // reference: missing file -> empty set, "ok" (descriptor.h:168-180)
-  const std::streamoff size = f.tellg();
-  f.seekg(0);
-  std::vector<uint8_t> raw((size_t)size);
-  if (size) f.read(reinterpret_cast<char*>(raw.data()), size);
-  for (int hdr : {8, 4}) {  // sizeof(size_t) of the writer: 8 on Linux x86-64, 4 in the shipped data/et files
-    if (size < hdr) continue;
-    uint64_t n = 0;
-    memcpy(&n, raw.data(), hdr);
-    if ((uint64_t)size == (uint64_t)hdr + n * MVGCUDA_DIM) {
-      out.assign(raw.begin() + hdr, raw.end());
-      rows = (int)n;
-      return true;
-    }
-  }
-  return size == 0;
-}
-
-bool load_feat_xy(const std::string& path, std::vector<float>& xy) {
-  xy.clear();
-  std::ifstream f(path.c_str());
-  if (!f.is_open()) return true;
-  float x, y, s, o;
-  while (f >> x >> y >> s >> o) { xy.push_back(x); xy.push_back(y); }
-  return !f.bad();
-}
-
 // "x y scale orientation" per feature (feature.h:117-133), parsed from a buffer that holds the whole file: the same token
 // rule as  in >> x >> y >> scale >> orientation  (whitespace-separated, stop at the first token that is not a number), an
 // order of magnitude faster than the stream extractors (std::from_chars rounds like strtof).  xy receives the first
