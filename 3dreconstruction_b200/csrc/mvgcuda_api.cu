@@ -37,7 +37,7 @@ static thread_local char g_create_error[512] = "";
     }                                                                                               \
   } while (0)
 
-constexpr float kDefaultPruneRho = 0.8f;
+constexpr float kDefaultPruneRho = 0.72f;  // profiles/r02w_rho_sweep.log: kernel time vs size of the second pass
 constexpr int kDefaultRescanRows = 1 << 20;  // 128 MB of gathered queries per second pass
 
 struct Arena {

@@ -235,7 +235,7 @@ class Context:
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._lib.mvgcuda_set_stream(self._h, C.c_void_p(cuda_stream)), "mvgcuda_set_stream")
 
-    def set_tuning(self, prune_rho: float = 0.8, rescan_rows: int = 0) -> None:
+    def set_tuning(self, prune_rho: float = 0.72, rescan_rows: int = 0) -> None:
         """Ratio-aware pruning knobs (results never depend on them): admission factor and rescan buffer rows."""
         self._check(self._lib.mvgcuda_set_tuning(self._h, C.c_float(prune_rho), int(rescan_rows)), "mvgcuda_set_tuning")
 

@@ -439,7 +439,7 @@ def run_ours(args):
                        "sharding": "replicated descriptor arena, contiguous cost-balanced split of the pair list, no collective",
                        "l2": "per step 0.13 GB of descriptors + 0.79 GB of per-query records stream through HBM, larger than the 126 MB L2; no explicit flush",
                        "matches_per_step_rank0": n_matches,
-                       "second_pass": f"{rescanned} of {len(my_pairs) * ROWS} queries of rank 0 matched twice per step (ambiguous after pruning, prune_rho 0.8); their time is inside the timed region, their ops are not credited",
+                       "second_pass": f"{rescanned} of {len(my_pairs) * ROWS} queries of rank 0 matched twice per step (ambiguous after pruning, default prune_rho 0.72); their time is inside the timed region, their ops are not credited",
                        "device": info["name"]},
             "clocks": clocks, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -78,7 +78,7 @@ int mvgcuda_set_stream(mvgcuda_ctx* ctx, void* cuda_stream);
 
 /* Tuning of the ratio-aware pruning of the pair / collection level (results never depend on it).
  * prune_rho in (0, 1]: a query that currently fails the ratio test only admits db rows with d <= prune_rho * d(best);
- * 1 = plain best-distance bound (no query is ever matched twice), default 0.8.  It is clamped from below to the ratio
+ * 1 = plain best-distance bound (no query is ever matched twice), default 0.72.  It is clamped from below to the ratio
  * of the call.  rescan_rows: rows of the buffer the ambiguous queries of a batch are gathered into (0 = default 2^20);
  * a batch with more of them is matched again through a bounded multi-round path (same results, one synchronisation). */
 int mvgcuda_set_tuning(mvgcuda_ctx* ctx, float prune_rho, int rescan_rows);
