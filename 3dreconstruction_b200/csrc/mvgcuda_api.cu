@@ -554,6 +554,7 @@ struct MatchRun {  // state of one match_pairs / match_collection call
   float gpu_ms = 0.f, knn_ms = 0.f;
   int knn_launches = 0, launches = 0;
   std::vector<char> seen;  // scratch of wait_for_images
+  long long total_records = 0, done_records = 0;  // queries of the whole call / of the finished batches
 };
 
 // Enqueue every kernel of the batch [p0, p1) into slot S.  No synchronisation with the compute stream.
@@ -650,9 +651,14 @@ static int finish_batch(mvgcuda_ctx* ctx, MatchRun& R, BatchSlot& S) {
   const int nb = S.nb;
   const long long nm = S.h_offsets.p[nb];
   const long long new_total = R.match_base + nm;
+  R.done_records += S.n_records;
   if ((size_t)std::max<long long>(new_total, 1) * 2 > ctx->r_matches.cap) {
+    // Grow ONCE to what the match density so far predicts for the whole call (+15 %), not step by step: page-locking is
+    // slow (~1 GB/s) and serialised across the GPUs of a box, and every step would copy what is already there.
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));  // copies into the old buffer finish before it moves
-    CU_CHECK(ctx, ctx->r_matches.reserve((size_t)std::max<long long>(new_total, 1) * 2 + (size_t)nm, (size_t)R.match_base * 2));
+    const double density = R.done_records > 0 ? (double)new_total / (double)R.done_records : 0.0;
+    const long long predicted = (long long)(density * (double)R.total_records * 1.15) + nm;
+    CU_CHECK(ctx, ctx->r_matches.reserve((size_t)std::max<long long>(std::max(new_total, predicted), 1) * 2, (size_t)R.match_base * 2));
   }
   if (nm > 0)
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->r_matches.p + R.match_base * 2, S.d_matches.p, nm * sizeof(int2), cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -690,6 +696,7 @@ static int match_pairs_impl(mvgcuda_ctx* ctx, int64_t n_pairs, const int32_t* pa
   ctx->repaired_batches = 0;
   MatchRun R;
   R.pairs = pairs; R.n_pairs = n_pairs; R.ratio_sq = ratio_sq; R.dedup_xy = dedup_xy;
+  for (int64_t p = 0; p < n_pairs; ++p) R.total_records += A.rows[pairs[2 * p + 1]];
   R.prune = ratio_sq <= 1.0f;
   R.rho = R.prune ? effective_rho(ctx, ratio_sq) : 1.0f;
   for (BatchSlot& S : ctx->slot) {
@@ -997,6 +1004,17 @@ int mvgcuda_stream_image(mvgcuda_ctx* ctx, int image, const uint8_t* desc, const
   CU_CHECK(ctx, cudaEventRecord(A.img_ev[image], st));
   A.streamed[image] = 1;
   A.ready[image] = 0;
+  return MVGCUDA_OK;
+}
+MVG_GUARD(ctx)
+
+int mvgcuda_stream_images(mvgcuda_ctx* ctx, int count, const int32_t* images, const uint8_t* const* desc, const float* const* feats_xy) try {
+  if (!ctx) return MVGCUDA_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!images || !desc))) { ctx->set_error("stream_images: bad list"); return MVGCUDA_ERR_INVALID; }
+  for (int k = 0; k < count; ++k) {
+    const int rc = mvgcuda_stream_image(ctx, images[k], desc[k], feats_xy ? feats_xy[k] : nullptr);
+    if (rc) return rc;
+  }
   return MVGCUDA_OK;
 }
 MVG_GUARD(ctx)

@@ -77,6 +77,7 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_host_free": (None, [C.c_void_p]),
     "mvgcuda_stream_begin": (C.c_int, [_ctx, C.c_int, _i32p]),
     "mvgcuda_stream_image": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_uint8), _f32p]),
+    "mvgcuda_stream_images": (C.c_int, [_ctx, C.c_int, _i32p, _u8pp, _f32pp]),
     "mvgcuda_stream_end": (C.c_int, [_ctx]),
     "mvgcuda_db_create": (C.c_int, [_ctx, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_void_p)]),
     "mvgcuda_db_destroy": (None, [_ctx, C.c_void_p]),
@@ -285,11 +286,16 @@ class Context:
         self._check(self._lib.mvgcuda_stream_begin(self._h, n, rows), "mvgcuda_stream_begin")
         fm = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy] if feats_xy is not None else None
         self._staged = (mats, fm)
-        for k in (order if order is not None else range(n)):
-            m = mats[k]
-            dp = m.ctypes.data_as(C.POINTER(C.c_uint8)) if m.shape[0] else None
-            fp = fm[k].ctypes.data_as(_f32p) if fm is not None and m.shape[0] else None
-            self._check(self._lib.mvgcuda_stream_image(self._h, int(k), dp, fp), "mvgcuda_stream_image")
+        ids = [int(k) for k in (order if order is not None else range(n))]
+        cnt = len(ids)
+        idx = (C.c_int32 * max(cnt, 1))(*ids)
+        # raw addresses (cheaper than a ctypes pointer object per array: this loop is host time in front of the match call)
+        dps = (C.c_void_p * max(cnt, 1))(*[mats[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
+        fps = None
+        if fm is not None:
+            fps = (C.c_void_p * max(cnt, 1))(*[fm[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
+        self._check(self._lib.mvgcuda_stream_images(self._h, cnt, idx, C.cast(dps, _u8pp), C.cast(fps, _f32pp) if fps is not None else None),
+                    "mvgcuda_stream_images")
         if wait:
             self.stream_end()
 

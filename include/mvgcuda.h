@@ -113,6 +113,9 @@ int mvgcuda_host_alloc(size_t bytes, void** out);
 void mvgcuda_host_free(void* p);
 int mvgcuda_stream_begin(mvgcuda_ctx* ctx, int n_images, const int32_t* rows);
 int mvgcuda_stream_image(mvgcuda_ctx* ctx, int image, const uint8_t* desc, const float* feats_xy);
+/* The same for a list of images in one call (desc[k] / feats_xy[k] belong to image images[k]; feats_xy may be NULL). */
+int mvgcuda_stream_images(mvgcuda_ctx* ctx, int count, const int32_t* images, const uint8_t* const* desc,
+                          const float* const* feats_xy);
 int mvgcuda_stream_end(mvgcuda_ctx* ctx);
 int mvgcuda_num_images(const mvgcuda_ctx* ctx);
 int mvgcuda_image_rows(const mvgcuda_ctx* ctx, int image); /* <0 on bad id */

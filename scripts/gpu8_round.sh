@@ -27,3 +27,4 @@ PY
 done
 timeout 300 python scripts/driver_multi_gpu_check.py 8 2>&1 | tail -6 | tee $OUT/${TAG}_driver_multi_gpu.log
 NIMG=${NIMG:-1000} ROWS=8000 GPUS=8 timeout 1200 python tests/tools/config4_files.py 2>&1 | tail -8 | tee $OUT/${TAG}_config4_files_8gpu.log
+timeout 300 python tests/tools/startup_probe.py 2>&1 | tail -10 | tee $OUT/${TAG}_startup_probe.log
