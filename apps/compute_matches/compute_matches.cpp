@@ -223,6 +223,14 @@ int main(int argc, char** argv) {
     }
   }
   if (opt.outdir.empty()) { std::cerr << "\nIt is an invalid output directory" << std::endl; return EXIT_FAILURE; }
+  // cuInit enumerates every visible GPU (5-6 s on a box with eight 180 GB devices, 0.3 s with one): with an explicit
+  // --gpus N and no CUDA_VISIBLE_DEVICES of the caller's, only the first N devices are made visible -- before the first
+  // CUDA call of the process.
+  if (opt.gpus > 0 && getenv("CUDA_VISIBLE_DEVICES") == NULL) {
+    std::string vis;
+    for (int g = 0; g < opt.gpus; ++g) vis += (g ? "," : "") + std::to_string(g);
+    setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+  }
   std::cout << " You called : \n" << argv[0] << "\n--imadir " << opt.imadir << "\n--outdir " << opt.outdir << "\n--distratio "
             << opt.dist_ratio << "\n--geometricModel " << opt.geometric_model << std::endl;
   if (!dir_exists(opt.outdir)) { std::cerr << "output directory " << opt.outdir << " does not exist" << std::endl; return EXIT_FAILURE; }

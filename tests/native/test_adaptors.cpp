@@ -1,5 +1,6 @@
 // test_adaptors.cpp -- the C++ drop-in adaptors (include/mvgcuda/*.h) against the REFERENCE'S OWN classes, in one
-// binary: ArrayMatcherCuda vs ArrayMatcherBruteForce, MatcherCudaAllInMemory vs MatcherAllInMemory.
+// binary: ArrayMatcherCuda vs ArrayMatcherBruteForce, MatcherCudaAllInMemory vs MatcherAllInMemory,
+// ImageCollectionGeometricFilterCuda vs ImageCollectionGeometricFilter (GeometricFilter_FMatrix_AC, images of 640 x 480).
 // Built by tests/native/build_native.sh where the reference tree is mounted (it needs the reference headers); the
 // binary travels to the GPU box.  Usage: test_adaptors <match_dir> <name1> <name2> ...   (names of images whose
 // .feat/.desc live in match_dir).  Exit code 0 and "ADAPTORS OK" on success.
@@ -22,7 +23,10 @@ using namespace mvg::utils;
 #include "mvg/feature/matcher_all_in_memory.h"
 #include "mvg/feature/matcher_brute_force.h"
 #include "mvg/feature/two_view_matches.h"
+#include "mvg/feature/geometric_filter.h"
+#include "mvg/multiview/fundamental_acransac.h"
 #include "mvgcuda/array_matcher_cuda.h"
+#include "mvgcuda/geometric_filter_cuda.h"
 #include "mvgcuda/matcher_cuda_all_in_memory.h"
 
 using namespace mvg::feature;
@@ -44,7 +48,7 @@ static std::vector<unsigned char> rnd(int rows, int alphabet, unsigned seed) {
 
 // the two-view entry GetPutativesMatches<DescriptorT, MatcherT> (two_view_matches.h:9-47, used by
 // apps/sift_match/sift_match.cpp:89-99) with the CUDA matcher as MatcherT, against the brute-force matcher.
-static void two_view(int nL, int nR, int alphabet, unsigned seed, float ratio) {
+static void two_view_entry(int nL, int nR, int alphabet, unsigned seed, float ratio) {
   std::vector<unsigned char> l = rnd(nL, alphabet, seed), r = rnd(nR, alphabet, seed + 1);
   std::vector<DescriptorT> L(nL), R(nR);
   for (int i = 0; i < nL; ++i) memcpy(L[i].getData(), l.data() + (size_t)i * 128, 128);
@@ -105,8 +109,8 @@ int main(int argc, char** argv) {
   array_level(1000, 513, 3, 2);
   array_level(2, 5, 2, 3);
   array_level(1, 4, 256, 4);   // k=2 > rows: both return false, outputs untouched
-  two_view(700, 650, 4, 21, 0.8f);
-  two_view(1500, 1200, 256, 22, 0.95f);
+  two_view_entry(700, 650, 4, 21, 0.8f);
+  two_view_entry(1500, 1200, 256, 22, 0.95f);
   {
     ArrayMatcherCuda<unsigned char, MetricT> gpu;
     CHECK(!gpu.Build(NULL, 0, 128));
@@ -143,6 +147,27 @@ int main(int argc, char** argv) {
       CHECK(s0.str() == s1.str());
       std::cout << "collection ratio " << ratio << ": " << m0.size() << " pairs, " << s0.str().size() << " bytes, identical="
                 << (s0.str() == s1.str()) << std::endl;
+      if (ratio == 0.6f) {
+        // the step after (compute_matches.cpp:250-268): the reference's filter with its never-seeded rand() against the GPU one
+        const std::vector<std::pair<size_t, size_t> > sizes(names.size(), std::make_pair((size_t)640, (size_t)480));
+        ImageCollectionGeometricFilter<FeatureT> ref_filter;
+        ImageCollectionGeometricFilterCuda<FeatureT> gpu_filter;
+        CHECK(ref_filter.LoadData(names, dir));
+        CHECK(gpu_filter.LoadData(names, dir));
+        PairWiseMatches g0, g1;
+        std::cout.rdbuf(sink.rdbuf());
+        srand(1);
+        ref_filter.Filter(mvg::multiview::GeometricFilter_FMatrix_AC(4.0), m0, g0, sizes);
+        std::cout.rdbuf(old);
+        gpu_filter.Filter(mvg::multiview::GeometricFilter_FMatrix_AC(4.0), m1, g1, sizes);
+        std::ostringstream t0, t1;
+        PairedIndexedMatchToStream(g0, t0);
+        PairedIndexedMatchToStream(g1, t1);
+        CHECK(g0.size() == g1.size());
+        CHECK(t0.str() == t1.str());
+        std::cout << "geometric filter (F, AC-RANSAC): " << g0.size() << " pairs kept, " << t0.str().size() << " bytes, identical="
+                  << (t0.str() == t1.str()) << std::endl;
+      }
     }
   }
   std::cout << (fails ? "ADAPTORS FAILED" : "ADAPTORS OK") << std::endl;
