@@ -4,6 +4,9 @@ import importlib, os, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("3dreconstruction_b200")
+PROBE = os.path.join(ROOT, "build", "startup_probe")
+if not os.path.exists(PROBE):  # nvcc is in the image (here and on the GPU box)
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-o", PROBE, os.path.join(ROOT, "tests", "tools", "startup_probe.cu"), "-lcuda"])
 for rep in range(3):
     print(subprocess.run([os.path.join(ROOT, "build", "startup_probe")], capture_output=True, text=True).stdout.strip(), flush=True)
 print("CUDA_VISIBLE_DEVICES=0:", subprocess.run([os.path.join(ROOT, "build", "startup_probe")], capture_output=True, text=True,
