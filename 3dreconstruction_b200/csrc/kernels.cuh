@@ -109,7 +109,7 @@ struct KnnParams {
 // CTA, so the constants of an image that arrives while earlier pairs are being matched do not wait for that kernel.
 __device__ __forceinline__ int ccol_index(int row) { return (row >> 8) * kTileC + (row & 255); }
 __host__ __device__ constexpr size_t ccol_ints(int arena_rows) {
-  return static_cast<size_t>(arena_rows / kTileDb) * kTileC + static_cast<size_t>(arena_rows / kHalfCols);
+  return static_cast<size_t>(arena_rows / kTileDb) * kTileC + static_cast<size_t>(arena_rows / kHalfCols) + 2;  // + 2: the epilogue prefetches one tile past an item's last
 }
 constexpr int kK1Rows = kChunk;  // rows per block of K1
 
@@ -440,10 +440,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
       const int qn = p.qcol[ccol_index(it.z + min(q_local, it.w - 1))] >> 8;  // ||q||^2 (dist = qn + t)
       int g1t = 0x7FFFFFFF, g2t = 0x7FFFFFFF, g1i = -1, g2i = -1;  // running best two (t-domain) of this thread's columns
       int T = kTInit;                                              // admit t <= T
-      const uint32_t bound_saddr = bound0 + (item_it & 1u) * (4u * kBlockQ);
+      const uint32_t bound_saddr = keep_reg(bound0 + (item_it & 1u) * (4u * kBlockQ));
       ptx::sts32(bound0 + ((item_it & 1u) ^ 1u) * (4u * kBlockQ), kTInit);  // idle slot (every part left the previous item at the barrier below)
-      const int* hm_ptr = p.hmin + (it.x >> 7) + g;  // min ||d||^2 of tile t's half g: hm_ptr[2 t]
-      int hm_next = __ldg(hm_ptr);
+      int hm_off = (it.x >> 7) + g;  // min ||d||^2 of tile t's half g: p.hmin[hm_off + 2 t]
+      int hm_next = __ldg(p.hmin + hm_off);
 
       // One tile in accumulator buffer (kBuf, g); kBuf is a compile-time constant: everything it indexes is a loop invariant.
 #define MVG_TILE_STEP(kBuf, t_expr)                                                                                       \
@@ -458,8 +458,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 32, v2);                                                         \
         ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 48, v3);                                                         \
         const int hm = hm_next;                                                                                            \
-        hm_ptr += 2;                                                                                                       \
-        if (t + 1 < ntiles) hm_next = __ldg(hm_ptr);                                                                       \
+        hm_off += 2;                                                                                                       \
+        hm_next = __ldg(p.hmin + hm_off); /* unconditional: the array is padded by one tile */                             \
         T = min(T, ptx::lds32_volatile(bound_saddr));                                                                      \
         ptx::tmem_ld_wait_for4(v0, v1, v2, v3);                                                                            \
         ptx::tc_fence_before();                                                                                            \
