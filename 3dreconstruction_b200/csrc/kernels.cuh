@@ -452,16 +452,16 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::mbar_wait_addr(kBuf ? full1 : full0, (ph >> kBuf) & 1u);                                                      \
         ph ^= (1u << kBuf);                                                                                                \
         ptx::tc_fence_after();                                                                                             \
-        int32_t v0[16], v1[16], v2[16], v3[16];                                                                            \
-        ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb, v0);                                                              \
-        ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 16, v1);                                                         \
-        ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 32, v2);                                                         \
-        ptx::tmem_ld_32x32b_x16(tslice + kBuf * kTileDb + 48, v3);                                                         \
+        int32_t va[32], vb[32]; /* two 32-column loads: chunks 0, 1 and 2, 3 */                                             \
+        ptx::tmem_ld_32x32b_x32(tslice + kBuf * kTileDb, va);                                                              \
+        ptx::tmem_ld_32x32b_x32(tslice + kBuf * kTileDb + 32, vb);                                                         \
+        const int32_t* const v0 = va; const int32_t* const v1 = va + 16;                                                   \
+        const int32_t* const v2 = vb; const int32_t* const v3 = vb + 16;                                                   \
         const int hm = hm_next;                                                                                            \
         hm_off += 2;                                                                                                       \
         hm_next = __ldg(p.hmin + hm_off); /* unconditional: the array is padded by one tile */                             \
         T = min(T, ptx::lds32_volatile(bound_saddr));                                                                      \
-        ptx::tmem_ld_wait_for4(v0, v1, v2, v3);                                                                            \
+        ptx::tmem_ld_wait_for2x32(va, vb);                                                                                 \
         ptx::tc_fence_before();                                                                                            \
         __syncwarp();                                                                                                      \
         if (lane == 0) ptx::mbar_arrive_cluster(kBuf ? empty1 : empty0); /* the buffer goes back to the MMA warp now */    \
