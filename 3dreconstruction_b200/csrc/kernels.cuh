@@ -452,16 +452,15 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 128 rows x 128 
         ptx::mbar_wait_addr(kBuf ? full1 : full0, (ph >> kBuf) & 1u);                                                      \
         ph ^= (1u << kBuf);                                                                                                \
         ptx::tc_fence_after();                                                                                             \
-        int32_t va[32], vb[32]; /* two 32-column loads: chunks 0, 1 and 2, 3 */                                             \
-        ptx::tmem_ld_32x32b_x32(tslice + kBuf * kTileDb, va);                                                              \
-        ptx::tmem_ld_32x32b_x32(tslice + kBuf * kTileDb + 32, vb);                                                         \
+        int32_t va[64]; /* the whole 64-column slice in one load */                                                         \
+        ptx::tmem_ld_32x32b_x64(tslice + kBuf * kTileDb, va);                                                              \
         const int32_t* const v0 = va; const int32_t* const v1 = va + 16;                                                   \
-        const int32_t* const v2 = vb; const int32_t* const v3 = vb + 16;                                                   \
+        const int32_t* const v2 = va + 32; const int32_t* const v3 = va + 48;                                              \
         const int hm = hm_next;                                                                                            \
         hm_off += 2;                                                                                                       \
         hm_next = __ldg(p.hmin + hm_off); /* unconditional: the array is padded by one tile */                             \
         T = min(T, ptx::lds32_volatile(bound_saddr));                                                                      \
-        ptx::tmem_ld_wait_for2x32(va, vb);                                                                                 \
+        ptx::tmem_ld_wait_for64(va);                                                                                       \
         ptx::tc_fence_before();                                                                                            \
         __syncwarp();                                                                                                      \
         if (lane == 0) ptx::mbar_arrive_cluster(kBuf ? empty1 : empty0); /* the buffer goes back to the MMA warp now */    \
