@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kGeoBatchPairs = 1024;        // active pairs per launch
 constexpr long long kGeoBatchMatches = 4ll << 20;
+constexpr int kGeoMaxMatchesPerPair = 16384;
 
 struct GeoState {
   DevBuf<GeoPairDev> d_pairs;
@@ -121,6 +122,9 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     }
     if (counts[p] > kSampleF) { active.push_back(p); n_max = std::max(n_max, counts[p]); }
   }
+  // every warp of an evaluation wave owns a candidate list of n_cap entries in global scratch (used when more than 256
+  // residuals lie under the threshold): bounded so that the scratch stays below ~1.5 GB
+  if (n_max > kGeoMaxMatchesPerPair) return fail(ctx, "geometric_filter: a pair with more than 16,384 putative matches is not supported");
   GEO_CHECK(ctx, G.r_counts.reserve(std::max<int64_t>(n_pairs, 1)));
   GEO_CHECK(ctx, G.r_offsets.reserve(n_pairs + 1));
   GEO_CHECK(ctx, G.r_matches.reserve(2));

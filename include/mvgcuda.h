@@ -216,6 +216,7 @@ int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* p
  *   pairs/counts/offsets/matches   the putative matches, laid out like mvgcuda_pair_matches (e.g. the result of
  *                mvgcuda_match_collection, or an imported matches.putative.txt); pairs in std::map order
  *   image_sizes  [n_images][2] = width, height of every uploaded image (lists.txt columns 2, 3)
+ * A pair may hold at most 16,384 putative matches (MVGCUDA_ERR_INVALID beyond).
  * The feature coordinates must have been set (mvgcuda_set_features / mvgcuda_stream_image).  The result (matches of every
  * pair in ascending-residual order, as the reference stores them) is owned by the context and valid until the next
  * geometric_filter / destroy; out->rescanned_queries holds the number of rand() values consumed. */
