@@ -120,7 +120,13 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       const int32_t* m = matches + 2 * (offsets[p] + k);
       if (m[0] < 0 || m[0] >= V.rows[i] || m[1] < 0 || m[1] >= V.rows[j]) return fail(ctx, "geometric_filter: match index out of range");
     }
-    if (counts[p] > kSampleF) { active.push_back(p); n_max = std::max(n_max, counts[p]); }
+    if (counts[p] > kSampleF) {
+      // the normalisation divides by sqrt(width * height) (conditioning.cpp:46-56): a missing size would give NaNs
+      if (image_sizes[2 * i] < 1 || image_sizes[2 * i + 1] < 1 || image_sizes[2 * j] < 1 || image_sizes[2 * j + 1] < 1)
+        return fail(ctx, "geometric_filter: image size (width, height) missing for an image with matches");
+      active.push_back(p);
+      n_max = std::max(n_max, counts[p]);
+    }
   }
   // every warp of an evaluation wave owns a candidate list of n_cap entries in global scratch (used when more than 256
   // residuals lie under the threshold): bounded so that the scratch stays below ~1.5 GB
