@@ -155,11 +155,17 @@ MVG_GEO_HD void rotate_pair(double& x, double& y, double c, double s) {
   y = -s * xi + c * yi;
 }
 
+// jacobi_svd9_sweeps: steps 2-4 of JacobiSVD::compute on a 9x9 work matrix W with V already initialised (identity for a
+// square input, the column permutation of the QR preconditioner for a tall one).
+MVG_GEO_HD void jacobi_svd9_sweeps(double* W, double* V);
 MVG_GEO_HD void jacobi_svd9_v(double* W, double* V) {
-  const double precision = 2.0 * DBL_EPSILON;
-  const double consider_as_zero = 2.0 * 4.9406564584124654e-324;  // 2 * denorm_min
   for (int i = 0; i < 81; ++i) V[i] = 0.0;
   for (int i = 0; i < 9; ++i) V[i + 9 * i] = 1.0;
+  jacobi_svd9_sweeps(W, V);
+}
+MVG_GEO_HD void jacobi_svd9_sweeps(double* W, double* V) {
+  const double precision = 2.0 * DBL_EPSILON;
+  const double consider_as_zero = 2.0 * 4.9406564584124654e-324;  // 2 * denorm_min
   double scale = 0.0;
   for (int i = 0; i < 81; ++i) { const double a = fabs(W[i]); if (a > scale) scale = a; }
   if (scale == 0.0) scale = 1.0;
@@ -286,6 +292,149 @@ MVG_GEO_HD int seven_point_models(const double* x1, const double* x2, double* W,
   const int nr = solve_cubic(P, roots);
   models_from_roots(V + 9 * 8, V + 9 * 7, roots, nr, F);
   return nr;
+}
+
+// ------------------------------------------------------------------------------------------ 4-point homography solver
+// homography::FourPointSolver::Solve (solver_homography_kernel.cpp:34-58): 16x9 action matrix (two rows per point, rows
+// 8..15 zero) -> Nullspace -> JacobiSVD<Matrix<double,16,9>>(L, ComputeFullV).  More rows than columns: Eigen first runs
+// its QR preconditioner, ColPivHouseholderQR (ColPivHouseholderQR.h compute(), Householder.h), then the two-sided Jacobi
+// on R with V initialised to the column permutation.  The sums inside are SSE2-vectorised in the reference, so their
+// association is fixed by Eigen's code and the 16-byte alignment of the operands (element (r, c) of the 16x9 column-major
+// matrix is aligned iff r is even):
+//   fixed 16-vector squaredNorm   Redux.h redux_vec_unroller: binary tree over the 8 packets, then lane 0 + lane 1
+//   dynamic tail squaredNorm      Redux.h:202-253 (LinearVectorizedTraversal, NoUnrolling) on the abs2 EXPRESSION, which has no
+//                                 direct access: packets start at element 0 whatever the address (unaligned loads), two
+//                                 packet accumulators, lane 0 + lane 1, then the odd tail scalar
+//   essential^T * bottom          coefficient-based product (all dimensions "small"): a plain sequential dot per column
+struct P2 { double a, b; };
+MVG_GEO_HD P2 p2add(P2 x, P2 y) { return P2{x.a + y.a, x.b + y.b}; }
+MVG_GEO_HD P2 p2sq(const double* v) { return P2{v[0] * v[0], v[1] * v[1]}; }
+
+// squaredNorm of the dynamic block x[0 .. size) whose element 0 sits at an address of parity `odd` (1: misaligned)
+MVG_GEO_HD double eig_sqnorm_dyn(const double* x, int size, int odd) {
+  const int aligned_start = odd < size ? odd : size;
+  const int aligned_size2 = ((size - aligned_start) / 4) * 4;
+  const int aligned_size = ((size - aligned_start) / 2) * 2;
+  const int aligned_end2 = aligned_start + aligned_size2, aligned_end = aligned_start + aligned_size;
+  double res;
+  if (aligned_size) {
+    P2 r0 = p2sq(x + aligned_start);
+    if (aligned_size > 2) {
+      P2 r1 = p2sq(x + aligned_start + 2);
+      for (int i = aligned_start + 4; i < aligned_end2; i += 4) { r0 = p2add(r0, p2sq(x + i)); r1 = p2add(r1, p2sq(x + i + 2)); }
+      r0 = p2add(r0, r1);
+      if (aligned_end > aligned_end2) r0 = p2add(r0, p2sq(x + aligned_end2));
+    }
+    res = r0.a + r0.b;
+    for (int i = 0; i < aligned_start; ++i) res = res + x[i] * x[i];
+    for (int i = aligned_end; i < size; ++i) res = res + x[i] * x[i];
+  } else {
+    res = x[0] * x[0];
+    for (int i = 1; i < size; ++i) res = res + x[i] * x[i];
+  }
+  return res;
+}
+// essential^T * bottom: with a 16x9 maximum size Eigen's product selector classifies all three dimensions as "small"
+// (GeneralProduct.h product_size_category: MaxSize is not Dynamic) and evaluates the product coefficient by coefficient,
+// the inner dimension being dynamic without vectorisation: res = l0 r0; res += l_i r_i in order (CoeffBasedProduct.h).
+MVG_GEO_HD double eig_coeff_dot(const double* lhs, const double* rhs, int depth) {
+  double res = lhs[0] * rhs[0];
+  for (int i = 1; i < depth; ++i) res += lhs[i] * rhs[i];
+  return res;
+}
+
+// x1, x2: the 4 sampled (normalised) correspondences, [4][2].  A: 144 doubles of scratch (16x9), W, V: 81 each.
+// H: the model, H(r, c) at [3 r + c] (Map<RMat3> of the null vector V.col(8)).
+MVG_GEO_HD void four_point_model(const double* x1, const double* x2, double* A, double* W, double* V, double* H) {
+  for (int i = 0; i < 144; ++i) A[i] = 0.0;
+  for (int i = 0; i < 4; ++i) {  // BuildActionMatrix, solver_homography_kernel.cpp:12-32
+    const double xx = x1[2 * i], xy = x1[2 * i + 1], yx = x2[2 * i], yy = x2[2 * i + 1];
+    int j = 2 * i;
+    A[j + 16 * 0] = xx; A[j + 16 * 1] = xy; A[j + 16 * 2] = 1.0;
+    A[j + 16 * 6] = -yx * xx; A[j + 16 * 7] = -yx * xy; A[j + 16 * 8] = -yx;
+    ++j;
+    A[j + 16 * 3] = xx; A[j + 16 * 4] = xy; A[j + 16 * 5] = 1.0;
+    A[j + 16 * 6] = -yy * xx; A[j + 16 * 7] = -yy * xy; A[j + 16 * 8] = -yy;
+  }
+  // ---- ColPivHouseholderQR<Matrix<double,16,9>>::compute
+  const int rows = 16, cols = 9;
+  double col_sq[9], temp[9];
+  int transp[9], perm[9];
+  for (int k = 0; k < cols; ++k) {  // fixed-size aligned column: tree over the 8 packets
+    const double* c = A + 16 * k;
+    const P2 t = p2add(p2add(p2add(p2sq(c), p2sq(c + 2)), p2add(p2sq(c + 4), p2sq(c + 6))),
+                       p2add(p2add(p2sq(c + 8), p2sq(c + 10)), p2add(p2sq(c + 12), p2sq(c + 14))));
+    col_sq[k] = t.a + t.b;
+  }
+  double mx = col_sq[0];
+  for (int k = 1; k < cols; ++k) if (col_sq[k] > mx) mx = col_sq[k];
+  const double threshold_helper = mx * (DBL_EPSILON * DBL_EPSILON) / static_cast<double>(rows);
+  int nonzero_pivots = cols;
+  for (int k = 0; k < cols; ++k) {
+    int big = 0;
+    double big_v = col_sq[k];
+    for (int j = 1; j < cols - k; ++j) if (col_sq[k + j] > big_v) { big_v = col_sq[k + j]; big = j; }
+    big += k;
+    big_v = eig_sqnorm_dyn(A + k + 16 * big, rows - k, 0);
+    col_sq[big] = big_v;
+    if (big_v < threshold_helper * static_cast<double>(rows - k)) {
+      nonzero_pivots = k;
+      for (int c = k; c < cols; ++c)  // bottomRightCorner(rows-k, cols-k).triangularView<StrictlyLower>().setZero()
+        for (int r = c + 1; r < rows; ++r) A[r + 16 * c] = 0.0;
+      break;
+    }
+    transp[k] = big;
+    if (k != big) {
+      for (int r = 0; r < rows; ++r) { const double t = A[r + 16 * k]; A[r + 16 * k] = A[r + 16 * big]; A[r + 16 * big] = t; }
+      const double t = col_sq[k]; col_sq[k] = col_sq[big]; col_sq[big] = t;
+    }
+    // makeHouseholderInPlace on col(k).tail(rows - k)
+    double* ck = A + k + 16 * k;
+    const int n = rows - k;
+    const double tail_sq = n == 1 ? 0.0 : eig_sqnorm_dyn(ck + 1, n - 1, 0);
+    const double c0 = ck[0];
+    double tau, beta;
+    if (tail_sq == 0.0) {
+      tau = 0.0; beta = c0;
+      for (int r = 1; r < n; ++r) ck[r] = 0.0;
+    } else {
+      beta = sqrt(c0 * c0 + tail_sq);
+      if (c0 >= 0.0) beta = -beta;
+      const double den = c0 - beta;
+      for (int r = 1; r < n; ++r) ck[r] = ck[r] / den;
+      tau = (beta - c0) / beta;
+    }
+    ck[0] = beta;
+    // applyHouseholderOnTheLeft on bottomRightCorner(rows - k, cols - k - 1) with essential = col(k).tail(rows - k - 1)
+    const int nc = cols - k - 1;
+    if (nc > 0) {
+      const double* ess = ck + 1;
+      for (int j = 0; j < nc; ++j) temp[j] = eig_coeff_dot(ess, A + (k + 1) + 16 * (k + 1 + j), n - 1);
+      for (int j = 0; j < nc; ++j) temp[j] += A[k + 16 * (k + 1 + j)];
+      for (int j = 0; j < nc; ++j) A[k + 16 * (k + 1 + j)] -= temp[j] * tau;
+      for (int j = 0; j < nc; ++j)
+        for (int r = 0; r < n - 1; ++r) A[(k + 1 + r) + 16 * (k + 1 + j)] -= temp[j] * (ess[r] * tau);
+    }
+    for (int j = 0; j < nc; ++j) col_sq[k + 1 + j] -= A[k + 16 * (k + 1 + j)] * A[k + 16 * (k + 1 + j)];
+  }
+  for (int i = 0; i < cols; ++i) perm[i] = i;
+  for (int k = 0; k < nonzero_pivots; ++k) { const int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+  // ---- JacobiSVD: work matrix = upper triangle of R, V = the permutation (V(perm[i], i) = 1)
+  for (int c = 0; c < 9; ++c)
+    for (int r = 0; r < 9; ++r) W[r + 9 * c] = r <= c ? A[r + 16 * c] : 0.0;
+  for (int i = 0; i < 81; ++i) V[i] = 0.0;
+  for (int i = 0; i < 9; ++i) V[perm[i] + 9 * i] = 1.0;
+  jacobi_svd9_sweeps(W, V);
+  for (int t = 0; t < 9; ++t) H[t] = V[t + 9 * 8];
+}
+
+// homography::AsymmetricError::Error (solver_homography_kernel.h:32-38): || x2 - dehomogenise(H (x1, 1)) ||^2
+MVG_GEO_HD double homography_error(const double* H, double x1, double y1, double x2, double y2) {
+  const double hx = (H[0] * x1 + H[1] * y1) + H[2] * 1.0;
+  const double hy = (H[3] * x1 + H[4] * y1) + H[5] * 1.0;
+  const double hz = (H[6] * x1 + H[7] * y1) + H[8] * 1.0;
+  const double dx = x2 - hx / hz, dy = y2 - hy / hz;
+  return dx * dx + dy * dy;
 }
 
 // ------------------------------------------------------------------------------------------ residual

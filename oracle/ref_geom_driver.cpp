@@ -85,6 +85,24 @@ int ref_seven_point(const double* x1, const double* x2, double* F) {
   return (int)models.size();
 }
 
+// homography::FourPointSolver::Solve on 4 correspondences ([4][2] each) -> H, row-major 3x3 (one model).
+int ref_four_point(const double* x1, const double* x2, double* H) {
+  Mat a(2, 4), b(2, 4);
+  for (int i = 0; i < 4; ++i) { a(0, i) = x1[2 * i]; a(1, i) = x1[2 * i + 1]; b(0, i) = x2[2 * i]; b(1, i) = x2[2 * i + 1]; }
+  std::vector<Mat3> models;
+  homography::FourPointSolver::Solve(a, b, &models);
+  for (size_t k = 0; k < models.size(); ++k)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) H[9 * k + 3 * r + c] = models[k](r, c);
+  return (int)models.size();
+}
+
+double ref_homography_error(const double* H, double x1, double y1, double x2, double y2) {
+  Mat3 M;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M(r, c) = H[3 * r + c];
+  return homography::AsymmetricError::Error(M, Vec2(x1, y1), Vec2(x2, y2));
+}
+
 // NormalizePoints(points, &out, &T, width, height) on n float points ([n][2]); T: row-major 3x3.
 void ref_normalize(const float* pts, int n, int width, int height, double* out, double* T) {
   Mat x(2, n), xn;

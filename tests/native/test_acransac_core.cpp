@@ -14,6 +14,8 @@ extern "C" {
 int ref_seven_point(const double* x1, const double* x2, double* F);
 void ref_normalize(const float* pts, int n, int width, int height, double* out, double* T);
 double ref_epipolar_error(const double* F, double x1, double y1, double x2, double y2);
+int ref_four_point(const double* x1, const double* x2, double* H);
+double ref_homography_error(const double* H, double x1, double y1, double x2, double y2);
 void ref_rand(unsigned seed, int n, unsigned* out);
 void ref_random_sample7(unsigned seed, int skip, int n, int* out);
 }
@@ -91,6 +93,27 @@ int main() {
     std::printf("seven-point: %ld coefficients compared, %ld differ in bits, %ld samples with a different model count "
                 "(1-root %ld, 3-root %ld), residual mismatches %ld\n", models, bits_diff, count_diff, one, three, err_diff);
     if (bits_diff || count_diff || err_diff) ++bad;
+  }
+  // 6. four-point homography solver (QR-preconditioned Jacobi SVD of the 16x9 action matrix) + its residual
+  {
+    std::uniform_real_distribution<double> u(-0.6, 0.6);
+    long coeffs = 0, bits_diff = 0, err_diff = 0;
+    double A[144], W[81], V[81];
+    for (int t = 0; t < 20000; ++t) {
+      double x1[8], x2[8];
+      for (int i = 0; i < 8; ++i) { x1[i] = u(rng); x2[i] = u(rng); }
+      if (t % 5 == 1) for (int i = 0; i < 8; ++i) x2[i] = x1[i] + 0.01 * u(rng);   // near-identity
+      if (t % 5 == 2) { x1[2] = x1[0]; x1[3] = x1[1]; }                              // duplicated point
+      if (t % 5 == 3) for (int i = 0; i < 4; ++i) x1[2 * i + 1] = 0.3 * x1[2 * i] + 0.1;  // collinear
+      double Hw[9], Hg[9];
+      ref_four_point(x1, x2, Hw);
+      four_point_model(x1, x2, A, W, V, Hg);
+      for (int k = 0; k < 9; ++k) { ++coeffs; if (!same_bits(Hw[k], Hg[k])) ++bits_diff; }
+      const double a = u(rng), b = u(rng), c = u(rng), d = u(rng);
+      if (!same_bits(ref_homography_error(Hw, a, b, c, d), homography_error(Hw, a, b, c, d))) ++err_diff;
+    }
+    std::printf("four-point: %ld coefficients compared, %ld differ in bits, residual mismatches %ld\n", coeffs, bits_diff, err_diff);
+    if (bits_diff || err_diff) ++bad;
   }
   std::printf(bad ? "ACRANSAC CORE FAILED\n" : "ACRANSAC CORE OK\n");
   return bad ? 1 : 0;
