@@ -345,7 +345,14 @@ MVG_GEO_HD double eig_coeff_dot(const double* lhs, const double* rhs, int depth)
 
 // x1, x2: the 4 sampled (normalised) correspondences, [4][2].  A: 144 doubles of scratch (16x9), W, V: 81 each.
 // H: the model, H(r, c) at [3 r + c] (Map<RMat3> of the null vector V.col(8)).
+MVG_GEO_HD void four_point_qr(const double* x1, const double* x2, double* A, double* W, double* V);
 MVG_GEO_HD void four_point_model(const double* x1, const double* x2, double* A, double* W, double* V, double* H) {
+  four_point_qr(x1, x2, A, W, V);
+  jacobi_svd9_sweeps(W, V);
+  for (int t = 0; t < 9; ++t) H[t] = V[t + 9 * 8];
+}
+// the action matrix and its QR preconditioner: leaves the Jacobi work matrix in W and the column permutation in V
+MVG_GEO_HD void four_point_qr(const double* x1, const double* x2, double* A, double* W, double* V) {
   for (int i = 0; i < 144; ++i) A[i] = 0.0;
   for (int i = 0; i < 4; ++i) {  // BuildActionMatrix, solver_homography_kernel.cpp:12-32
     const double xx = x1[2 * i], xy = x1[2 * i + 1], yx = x2[2 * i], yy = x2[2 * i + 1];
@@ -424,8 +431,6 @@ MVG_GEO_HD void four_point_model(const double* x1, const double* x2, double* A, 
     for (int r = 0; r < 9; ++r) W[r + 9 * c] = r <= c ? A[r + 16 * c] : 0.0;
   for (int i = 0; i < 81; ++i) V[i] = 0.0;
   for (int i = 0; i < 9; ++i) V[perm[i] + 9 * i] = 1.0;
-  jacobi_svd9_sweeps(W, V);
-  for (int t = 0; t < 9; ++t) H[t] = V[t + 9 * 8];
 }
 
 // homography::AsymmetricError::Error (solver_homography_kernel.h:32-38): || x2 - dehomogenise(H (x1, 1)) ||^2
@@ -448,10 +453,11 @@ MVG_GEO_HD double epipolar_error(const double* F, double x1, double y1, double x
   return (dot * dot) / (fx0 * fx0 + fx1 * fx1);
 }
 
-// One term of bestNFA (estimator_acransac.h:86-91), multError = 0.5 (point-to-line):
-//   logalpha = logalpha0 + 0.5 * log10(e + FLT_MIN);  NFA = loge0 + logalpha * (k - 7) + logc_n[k] + logc_k[k]
-MVG_GEO_HD double nfa_term(double logalpha0, double loge0, double err, int k, int sample_size, float logc_n_k, float logc_k_k) {
-  const double logalpha = logalpha0 + 0.5 * log10(err + static_cast<double>(FLT_MIN));
+// One term of bestNFA (estimator_acransac.h:86-91); mult_error = 0.5 for point-to-line residuals (F), 1.0 for
+// point-to-point ones (H) (estimator_acransac_kernel_adaptator.h:92):
+//   logalpha = logalpha0 + mult_error * log10(e + FLT_MIN);  NFA = loge0 + logalpha * (k - sample_size) + logc_n[k] + logc_k[k]
+MVG_GEO_HD double nfa_term(double logalpha0, double loge0, double mult_error, double err, int k, int sample_size, float logc_n_k, float logc_k_k) {
+  const double logalpha = logalpha0 + mult_error * log10(err + static_cast<double>(FLT_MIN));
   return loge0 + logalpha * static_cast<double>(k - sample_size) + logc_n_k + logc_k_k;
 }
 

@@ -23,7 +23,8 @@
 namespace mvgcuda {
 namespace geo {
 
-constexpr int kSampleF = 7;  // SevenPointSolver::MINIMUM_SAMPLES
+constexpr int kSampleF = 7;  // SevenPointSolver::MINIMUM_SAMPLES (fundamental matrix)
+constexpr int kSampleH = 4;  // homography::FourPointSolver::MINIMUM_SAMPLES
 
 struct AcState {
   double min_nfa;      // +inf: no model yet
@@ -34,11 +35,14 @@ struct AcState {
   int index_it, index_model, n_index;  // vec_index = first n_index inliers of (index_it, index_model); index_it < 0: identity
   int extend_to;       // > 0: nothing found in the first phase, the loop grows one iteration at a time up to this bound
   int done;
+  int sample;          // MINIMUM_SAMPLES of the model (7: fundamental matrix, 4: homography)
+  int pad;
 };
 
 MVG_GEO_HD double ac_inf() { return __builtin_huge_val(); }
 
-MVG_GEO_HD void ac_init(AcState& S, int n_data, int max_iterations) {
+MVG_GEO_HD void ac_init(AcState& S, int n_data, int max_iterations, int sample_size = kSampleF) {
+  S.sample = sample_size; S.pad = 0;
   S.min_nfa = ac_inf();
   S.best_it = -1; S.best_model = 0; S.n_inl = 0;
   S.iter = 0;
@@ -46,7 +50,7 @@ MVG_GEO_HD void ac_init(AcState& S, int n_data, int max_iterations) {
   S.iter_num = max_iterations - S.reserve;
   S.index_it = -1; S.index_model = 0; S.n_index = n_data;
   S.extend_to = 0;
-  S.done = (n_data <= kSampleF) ? 1 : 0;      // :137-138 (nothing is drawn from rand())
+  S.done = (n_data <= sample_size) ? 1 : 0;   // :137-138 (nothing is drawn from rand())
   if (S.done) S.iter_num = 0;
 }
 
@@ -107,10 +111,10 @@ MVG_GEO_HD int ac_account(AcState& S, const Range& R) {
 }
 
 // What ACRANSAC + GeometricFilter_FMatrix_AC::Fit leave (fundamental_acransac.h:44-47): the inliers are kept only for a
-// meaningful model (minNFA < 0, :240-241) with at least 2.5 x 7 of them.
+// meaningful model (minNFA < 0, :240-241) with at least 2.5 x MINIMUM_SAMPLES of them (homography_acransac.h:55-57 alike).
 MVG_GEO_HD int ac_final_inliers(const AcState& S) {
   if (!(S.min_nfa < 0.0)) return 0;
-  return (static_cast<double>(S.n_inl) < kSampleF * 2.5) ? 0 : S.n_inl;
+  return (static_cast<double>(S.n_inl) < S.sample * 2.5) ? 0 : S.n_inl;
 }
 
 }  // namespace geo
@@ -128,9 +132,11 @@ struct PairGeo {
   const double* x2;
   double max_threshold;  // precision * N2(0,0)^2 (estimator_acransac.h:140-142)
   double logalpha0;      // log10(2 D / A / N2(0,0)) (estimator_acransac_kernel_adaptator.h:53-58)
-  double loge0;          // log10(MAX_MODELS * (n - 7)) (estimator_acransac.h:153)
-  const float* logc_n;   // [n + 1] log10 C(n, k)   (makelogcombi_n, :50-56)
-  const float* logc_k;   // [n + 1] log10 C(k, 7)   (makelogcombi_k, :59-65)
+  double loge0;          // log10(MAX_MODELS * (n - sample)) (estimator_acransac.h:153)
+  const float* logc_n;   // [n + 1] log10 C(n, k)        (makelogcombi_n, :50-56)
+  const float* logc_k;   // [n + 1] log10 C(k, sample)   (makelogcombi_k, :59-65)
+  int sample;            // MINIMUM_SAMPLES
+  double mult_error;     // 0.5 point-to-line, 1.0 point-to-point
 };
 
 struct Cand { double e; int i; };
@@ -140,9 +146,9 @@ MVG_GEO_HD bool cand_less(const Cand& a, const Cand& b) { return a.e < b.e || (!
 // bestNFA (estimator_acransac.h:73-96) over the sorted candidates (all residuals <= max_threshold): strict <, ascending k.
 MVG_GEO_HD void best_nfa_scalar(const PairGeo& P, const Cand* list, int m, double& nfa, int& k_best) {
   nfa = ac_inf();
-  k_best = kSampleF;
-  for (int k = kSampleF + 1; k <= m; ++k) {
-    const double v = nfa_term(P.logalpha0, P.loge0, list[k - 1].e, k, kSampleF, P.logc_n[k], P.logc_k[k]);
+  k_best = P.sample;
+  for (int k = P.sample + 1; k <= m; ++k) {
+    const double v = nfa_term(P.logalpha0, P.loge0, P.mult_error, list[k - 1].e, k, P.sample, P.logc_n[k], P.logc_k[k]);
     if (v < nfa) { nfa = v; k_best = k; }
   }
 }

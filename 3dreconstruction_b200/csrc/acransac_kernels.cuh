@@ -88,6 +88,9 @@ struct GeoBatchDev {
   const uint32_t* stream;   // stream[k] = rand() value number stream_base + k of the process
   long long stream_base;
   int max_iterations;
+  int model;                // 0: fundamental matrix (7-point solver, point-to-line residual), 1: homography (4 points, point-to-point)
+  int sample;               // MINIMUM_SAMPLES of the model: rand() values drawn per iteration
+  double mult_error;        // exponent of the residual in the NFA: 0.5 / 1.0
   int it_stride;            // max_iterations + 8: per-slot stride of the per-iteration arrays
   int n_max;                // per-slot stride of vec_index
   int n_cap;                // power of two >= n_max: stride of the candidate-list scratch
@@ -169,7 +172,7 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
       double e = 0.0;
       if (i < P.n) {
         const double2 a = x1[i], b = x2[i];
-        e = epipolar_error(f, a.x, a.y, b.x, b.y);
+        e = B.model ? homography_error(f, a.x, a.y, b.x, b.y) : epipolar_error(f, a.x, a.y, b.x, b.y);
         keep = e <= P.max_threshold;
       }
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
@@ -204,13 +207,13 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
   return m;
 }
 
-// bestNFA over the sorted candidates (estimator_acransac.h:73-96): minimum over k = 8 .. m, lowest k among equal values.
+// bestNFA over the sorted candidates (estimator_acransac.h:73-96): minimum over k = sample + 1 .. m, lowest k among equal values.
 __device__ __forceinline__ void best_nfa_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* e, int m, int lane, double& nfa, int& k_best) {
   double v = ac_inf();
   int kb = 0x7fffffff;
   const float* lcn = B.logc_pool + P.logc_off;
-  for (int k = kSampleF + 1 + lane; k <= m; k += 32) {
-    const double t = nfa_term(P.logalpha0, P.loge0, e[k - 1], k, kSampleF, lcn[k], B.logc_k[k]);
+  for (int k = B.sample + 1 + lane; k <= m; k += 32) {
+    const double t = nfa_term(P.logalpha0, P.loge0, B.mult_error, e[k - 1], k, B.sample, lcn[k], B.logc_k[k]);
     if (t < v) { v = t; kb = k; }
   }
 #pragma unroll
@@ -220,16 +223,21 @@ __device__ __forceinline__ void best_nfa_warp(const GeoBatchDev& B, const GeoPai
     if (ov < v || (ov == v && ok < kb)) { v = ov; kb = ok; }
   }
   nfa = v;
-  k_best = v < ac_inf() ? kb : kSampleF;
+  k_best = v < ac_inf() ? kb : B.sample;
 }
 
 // jacobi_svd9_v (acransac_core.cuh) with the warp cooperating: the 2x2 step is computed by every lane (same inputs from
 // shared memory, same bits), lanes 0-8 then rotate one element pair of the two rows / columns of W each and lanes 9-17 one
 // element pair of V's columns.  Per element exactly the scalar version's operations, so V is bit-identical to it.
+__device__ __forceinline__ void jacobi_svd9_sweeps_warp(double* W, double* V, int lane);
 __device__ __forceinline__ void jacobi_svd9_v_warp(double* W, double* V, int lane) {
+  for (int i = lane; i < 81; i += 32) V[i] = (i % 10 == 0) ? 1.0 : 0.0;
+  jacobi_svd9_sweeps_warp(W, V, lane);
+}
+// the sweeps on a work matrix whose V is already initialised (identity, or the QR preconditioner's column permutation)
+__device__ __forceinline__ void jacobi_svd9_sweeps_warp(double* W, double* V, int lane) {
   const double precision = 2.0 * DBL_EPSILON;
   const double consider_as_zero = 2.0 * 4.9406564584124654e-324;
-  for (int i = lane; i < 81; i += 32) V[i] = (i % 10 == 0) ? 1.0 : 0.0;
   double scale = 0.0;
   for (int i = lane; i < 81; i += 32) { const double a = fabs(W[i]); if (a > scale) scale = a; }
 #pragma unroll
@@ -292,7 +300,7 @@ __device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, co
     double* e;
     int* idx;
     const int m = model_candidates_warp(B, P, ws.F + 9 * k, ws, ge, gi, lane, e, idx);
-    if (m > kSampleF) {
+    if (m > B.sample) {
       double v;
       int kb;
       best_nfa_warp(B, P, e, m, lane, v, kb);
@@ -326,38 +334,64 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   WarpScratch& ws = scratch[warp];
   double* ge = B.g_e + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
   int* gi = B.g_i + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
-  if (lane == 0) {
-    const uint32_t* r7 = B.stream + (R.offset + static_cast<long long>(kSampleF) * it - B.stream_base);
-    uint32_t r[kSampleF];
-    for (int q = 0; q < kSampleF; ++q) r[q] = r7[q];
-    int s[kSampleF];
-    random_sample<kSampleF>(r, R.n_index, s);
-    for (int i = 0; i < 81; ++i) ws.W[i] = 0.0;
-    for (int q = 0; q < kSampleF; ++q) {  // EncodeEpipolarEquation (seven_point_basis)
-      const int id = identity ? s[q] : V.vec_index[s[q]];
-      const double2 a = B.x1[P.m_off + id], b = B.x2[P.m_off + id];
-      ws.W[q + 9 * 0] = b.x * a.x; ws.W[q + 9 * 1] = b.x * a.y; ws.W[q + 9 * 2] = b.x;
-      ws.W[q + 9 * 3] = b.y * a.x; ws.W[q + 9 * 4] = b.y * a.y; ws.W[q + 9 * 5] = b.y;
-      ws.W[q + 9 * 6] = a.x;       ws.W[q + 9 * 7] = a.y;       ws.W[q + 9 * 8] = 1.0;
+  const uint32_t* rs = B.stream + (R.offset + static_cast<long long>(B.sample) * it - B.stream_base);
+  if (B.model == 0) {
+    if (lane == 0) {
+      uint32_t r[kSampleF];
+      for (int q = 0; q < kSampleF; ++q) r[q] = rs[q];
+      int s[kSampleF];
+      random_sample<kSampleF>(r, R.n_index, s);
+      for (int i = 0; i < 81; ++i) ws.W[i] = 0.0;
+      for (int q = 0; q < kSampleF; ++q) {  // EncodeEpipolarEquation (seven_point_basis)
+        const int id = identity ? s[q] : V.vec_index[s[q]];
+        const double2 a = B.x1[P.m_off + id], b = B.x2[P.m_off + id];
+        ws.W[q + 9 * 0] = b.x * a.x; ws.W[q + 9 * 1] = b.x * a.y; ws.W[q + 9 * 2] = b.x;
+        ws.W[q + 9 * 3] = b.y * a.x; ws.W[q + 9 * 4] = b.y * a.y; ws.W[q + 9 * 5] = b.y;
+        ws.W[q + 9 * 6] = a.x;       ws.W[q + 9 * 7] = a.y;       ws.W[q + 9 * 8] = 1.0;
+      }
+    }
+    __syncwarp();
+    jacobi_svd9_v_warp(ws.W, ws.V, lane);
+    if (lane == 0) {
+      double Pc[4], roots[3];
+      cubic_from_null_vectors(ws.V + 9 * 8, ws.V + 9 * 7, Pc);
+      const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
+      models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
+      ws.n_models = nr;
+      double* bs = V.basis + static_cast<size_t>(it) * kBasisDoubles;
+      for (int q = 0; q < 9; ++q) { bs[q] = ws.V[9 * 8 + q]; bs[9 + q] = ws.V[9 * 7 + q]; }
+      for (int q = 0; q < 4; ++q) bs[18 + q] = Pc[q];
+      double* out = V.models + static_cast<size_t>(it) * 27;
+      for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
+    }
+  } else {
+    // homography: no transcendental anywhere (QR preconditioner + Jacobi: +, -, *, /, sqrt), so the device model IS the
+    // reference's model bit for bit and nothing ever has to be re-evaluated with host values
+    if (lane == 0) {
+      uint32_t r[kSampleH];
+      for (int q = 0; q < kSampleH; ++q) r[q] = rs[q];
+      int s[kSampleH];
+      random_sample<kSampleH>(r, R.n_index, s);
+      double a[2 * kSampleH], b[2 * kSampleH];
+      for (int q = 0; q < kSampleH; ++q) {
+        const int id = identity ? s[q] : V.vec_index[s[q]];
+        const double2 u = B.x1[P.m_off + id], w = B.x2[P.m_off + id];
+        a[2 * q] = u.x; a[2 * q + 1] = u.y; b[2 * q] = w.x; b[2 * q + 1] = w.y;
+      }
+      four_point_qr(a, b, ws.le /* 144 doubles of scratch: the candidate list is not in use yet */, ws.W, ws.V);
+    }
+    __syncwarp();
+    jacobi_svd9_sweeps_warp(ws.W, ws.V, lane);
+    if (lane == 0) {
+      for (int q = 0; q < 9; ++q) ws.F[q] = ws.V[q + 9 * 8];
+      ws.n_models = 1;
+      double* out = V.models + static_cast<size_t>(it) * 27;
+      for (int q = 0; q < 9; ++q) out[q] = ws.F[q];
     }
   }
   __syncwarp();
-  jacobi_svd9_v_warp(ws.W, ws.V, lane);
-  if (lane == 0) {
-    double Pc[4], roots[3];
-    cubic_from_null_vectors(ws.V + 9 * 8, ws.V + 9 * 7, Pc);
-    const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
-    models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
-    ws.n_models = nr;
-    double* bs = V.basis + static_cast<size_t>(it) * kBasisDoubles;
-    for (int q = 0; q < 9; ++q) { bs[q] = ws.V[9 * 8 + q]; bs[9 + q] = ws.V[9 * 7 + q]; }
-    for (int q = 0; q < 4; ++q) bs[18 + q] = Pc[q];
-    double* out = V.models + static_cast<size_t>(it) * 27;
-    for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
-  }
-  __syncwarp();
   const IterRes r = evaluate_models_warp(B, P, ws, ws.n_models, ge, gi, lane);
-  if (lane == 0) { V.res[it] = r; V.exact[it] = 0; }
+  if (lane == 0) { V.res[it] = r; V.exact[it] = B.model; }  // a homography model needs no second look
 }
 
 // The same iterations again with the roots the host's C library computed for their cubics: bit-identical to the reference.
@@ -534,7 +568,7 @@ __global__ void geo_selftest_kernel(int n, const double* __restrict__ x1 /*[n][1
   for (int k = 0; k < 27; ++k) F[27 * t + k] = f[k];
   const double e = epipolar_error(f, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
   err[t] = e;
-  nfa[t] = nfa_term(-1.25, 2.5, e, 8 + (t & 63), kSampleF, 3.5f, 1.25f);
+  nfa[t] = nfa_term(-1.25, 2.5, 0.5, e, 8 + (t & 63), kSampleF, 3.5f, 1.25f);
 }
 
 }  // namespace geo

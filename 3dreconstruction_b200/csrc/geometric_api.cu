@@ -52,6 +52,7 @@ struct GeoState {
   PinnedBuf<int> r_matches;
   // log tables (host copies; the pool only grows within a call)
   std::vector<float> logc_k;
+  int logc_k_sample = 0;  // the MINIMUM_SAMPLES the table was built for
   std::vector<float> logc_pool;
   std::map<int, int> logc_off;  // n -> offset in the pool
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -95,7 +96,12 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
                                         const int32_t* image_sizes, mvgcuda_pair_matches* out) try {
   if (!ctx) return MVGCUDA_ERR_INVALID;
   if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !counts || !offsets || !matches)) || !image_sizes) return fail(ctx, "geometric_filter: null argument");
-  if (model != 'f') return fail(ctx, "geometric_filter: only the fundamental-matrix model ('f') is built (SURVEY.md 8(f)-1)");
+  if (model != 'f' && model != 'h')
+    return fail(ctx, "geometric_filter: only the fundamental-matrix ('f') and homography ('h') models are built (SURVEY.md 8(f)-1)");
+  // GeometricFilter_FMatrix_AC: 7 points, <= 3 models, point-to-line residual; GeometricFilter_HMatrix_AC: 4 points, 1 model,
+  // point-to-point residual (homography_acransac.h:35-46)
+  const int sample = model == 'f' ? kSampleF : kSampleH;
+  const int max_models = model == 'f' ? kMaxModelsF : 1;
   if (iterations < 10 || iterations > (1 << 20)) return fail(ctx, "geometric_filter: iterations out of range");
   const CtxView V = ctx_view(ctx);
   if (!V.feats) return fail(ctx, "geometric_filter: call mvgcuda_set_features (or stream the features) first");
@@ -120,7 +126,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       const int32_t* m = matches + 2 * (offsets[p] + k);
       if (m[0] < 0 || m[0] >= V.rows[i] || m[1] < 0 || m[1] >= V.rows[j]) return fail(ctx, "geometric_filter: match index out of range");
     }
-    if (counts[p] > kSampleF) {
+    if (counts[p] > sample) {
       // the normalisation divides by sqrt(width * height) (conditioning.cpp:46-56): a missing size would give NaNs
       if (image_sizes[2 * i] < 1 || image_sizes[2 * i + 1] < 1 || image_sizes[2 * j] < 1 || image_sizes[2 * j + 1] < 1)
         return fail(ctx, "geometric_filter: image size (width, height) missing for an image with matches");
@@ -137,9 +143,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   for (int64_t p = 0; p < n_pairs; ++p) G.r_counts.p[p] = 0;
 
   // ---- log tables through the C library's log10, accumulated exactly as logcombi does (estimator_acransac.h:39-65)
-  if ((int)G.logc_k.size() < n_max + 1) {
+  if ((int)G.logc_k.size() < n_max + 1 || G.logc_k_sample != sample) {
     G.logc_k.resize(n_max + 1);
-    make_logc_k(kSampleF, n_max, G.logc_k.data());
+    make_logc_k(sample, n_max, G.logc_k.data());
+    G.logc_k_sample = sample;
   }
   G.logc_pool.clear();
   G.logc_off.clear();
@@ -234,8 +241,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       D.max_threshold = std::isinf(precision) ? precision : precision * D.N2.d * D.N2.d;
       const double diag = sqrt(wj * (double)wj + hj * (double)hj);
       const double area = wj * (double)hj;
-      D.logalpha0 = log10(2.0 * diag / area / D.N2.d);
-      D.loge0 = log10((double)kMaxModelsF * (size_t)(D.n - kSampleF));
+      // point to line: ratio of the image diagonal over its area; point to point: unit circle over the image area
+      // (estimator_acransac_kernel_adaptator.h:53-63)
+      D.logalpha0 = model == 'f' ? log10(2.0 * diag / area / D.N2.d) : log10(M_PI / (wj * (double)hj) / (D.N2.d * D.N2.d));
+      D.loge0 = log10((double)max_models * (size_t)(D.n - sample));
       G.h_pairs.p[k] = D;
       for (int q = 0; q < D.n; ++q) {
         const int32_t* m = matches + 2 * (offsets[p] + q);
@@ -244,7 +253,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       mo += D.n;
     }
     // stream window [offset, offset + 7 * iterations * nb)
-    const long long need_end = offset + (long long)kSampleF * iterations * nb;
+    const long long need_end = offset + (long long)sample * iterations * nb;
     if (offset > win_base) {
       window.erase(window.begin(), window.begin() + (size_t)(offset - win_base));
       win_base = offset;
@@ -263,7 +272,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GeoBatchDev B;
     B.pairs = G.d_pairs.p; B.n_pairs = nb; B.matches = G.d_matches.p; B.feats = V.feats; B.x1 = G.d_x1.p; B.x2 = G.d_x2.p;
     B.logc_pool = G.d_logc_pool.p; B.logc_k = G.d_logc_k.p; B.stream = G.d_stream.p; B.stream_base = offset;
-    B.max_iterations = iterations; B.it_stride = it_stride; B.n_max = n_max; B.n_cap = n_cap;
+    B.max_iterations = iterations; B.model = model == 'f' ? 0 : 1; B.sample = sample; B.mult_error = model == 'f' ? 0.5 : 1.0; B.it_stride = it_stride; B.n_max = n_max; B.n_cap = n_cap;
     B.res = G.d_res.p; B.models = G.d_models.p; B.basis = G.d_basis.p; B.exact = G.d_exact.p; B.vec_index = G.d_vec_index.p;
     B.state = G.d_state.p; B.round = G.d_round.p; B.decide = G.d_decide.p; B.g_e = G.d_ge.p; B.g_i = G.d_gi.p;
     B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p; B.out_iters = G.d_out_iters.p;
@@ -289,7 +298,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kFree) { sl = q; break; }
         if (sl < 0) break;
         AcState S0;
-        ac_init(S0, G.h_pairs.p[next_admit].n, iterations);
+        ac_init(S0, G.h_pairs.p[next_admit].n, iterations, sample);
         RoundInfo R0;
         R0.pair = next_admit; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = chain_offset;
         G.h_state.p[sl] = S0;
@@ -342,7 +351,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         HostSlot& H = slots[q];
         const DecideOut& D = G.h_decide.p[q];
         if (q == chain_tail && D.iters_final >= 0) {
-          chain_offset += (long long)kSampleF * D.iters_final;
+          chain_offset += (long long)sample * D.iters_final;
           chain_tail = -1;
         }
         if (D.status == 1) {

@@ -368,9 +368,10 @@ class Context:
     # -- the step after the path: AC-RANSAC geometric filter (geometric_filter.h:37-102)
     def geometric_filter(self, putative: "PairMatches", image_sizes: Sequence[Tuple[int, int]], model: str = "f", precision: float = 4.0,
                          iterations: int = 4096, seed: int = 1) -> "PairMatches":
-        """ImageCollectionGeometricFilter::Filter(GeometricFilter_FMatrix_AC(precision, iterations)) over `putative` (pairs in
-        std::map order; features already set).  seed=1 is the reference's never-seeded rand() stream.  Returns the kept
-        matches per pair in ascending-residual order; timing['rand_consumed'] = rand() values drawn."""
+        """ImageCollectionGeometricFilter::Filter(GeometricFilter_FMatrix_AC(precision, iterations)) -- model "f" -- or
+        GeometricFilter_HMatrix_AC -- model "h" -- over `putative` (pairs in std::map order; features already set).  seed=1
+        is the reference's never-seeded rand() stream.  Returns the kept matches per pair in ascending-residual order;
+        timing['rand_consumed'] = rand() values drawn.  The essential-matrix functor ("e") is not built: error."""
         pairs = np.ascontiguousarray(putative.pairs, dtype=np.int32).reshape(-1, 2)
         counts = np.ascontiguousarray(putative.counts, dtype=np.int32)
         offsets = np.ascontiguousarray(putative.offsets, dtype=np.int64)

@@ -22,11 +22,12 @@
 //   3. the i < j pair list is cut into contiguous, cost-balanced (rows_i * rows_j) shards, one per GPU; every GPU runs
 //      rows 7-13 of the path on its shard (mvgcuda_match_collection; batches pipelined inside the library);
 //   4. the text of every shard is formatted concurrently and written in pair order.
-//   5. -g f: the AC-RANSAC fundamental-matrix filter (compute_matches.cpp:250-318, GeometricFilter_FMatrix_AC(4.0)) runs
-//      on GPU 0 over the putative matches (fresh or imported) and writes <outdir>/matches.f.txt; the reference's rand()
-//      stream is never seeded (== srand(1)) and is consumed pair after pair in map order -- reproduced.
+//   5. -g f / -g h: the AC-RANSAC filter (compute_matches.cpp:250-318, GeometricFilter_FMatrix_AC(4.0) resp.
+//      GeometricFilter_HMatrix_AC(4.0)) runs on GPU 0 over the putative matches (fresh or imported) and writes
+//      <outdir>/matches.f.txt resp. matches.h.txt; the reference's rand() stream is never seeded (== srand(1)) and is
+//      consumed pair after pair in map order -- reproduced.
 // Out of scope of this build: SIFT extraction (the stage before: .feat/.desc must exist) and the
-// essential / homography variants of the filter (-g e, the reference's default, needs K.txt; -g h): they stop after the
+// essential variant of the filter (-g e, the reference's default, needs K.txt and the 5-point solver): it stops after the
 // putative stage with a message.
 #include <algorithm>
 #include <atomic>
@@ -242,7 +243,8 @@ int main(int argc, char** argv) {
     return EXIT_FAILURE;
   }
   const std::string putative = opt.outdir + "/matches.putative.txt";
-  const bool filter_f = opt.geometric_model == "f";
+  const bool filter_f = opt.geometric_model == "f" || opt.geometric_model == "h";  // the models built on the GPU
+  const char geo_model = opt.geometric_model == "h" ? 'h' : 'f';
   const bool resumed = file_exists(putative);
   ImportedMatches im;
   if (resumed) {  // compute_matches.cpp:230-234
@@ -250,7 +252,7 @@ int main(int argc, char** argv) {
     std::cout << std::endl << "PUTATIVE MATCHES -- PREVIOUS RESULTS LOADED" << std::endl
               << im.pairs << " pairs, " << im.matches << " putative matches imported from " << putative << "; matching skipped" << std::endl;
     if (!filter_f) {
-      std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f is)" << std::endl;
+      std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f and -g h are)" << std::endl;
       return EXIT_SUCCESS;
     }
   }
@@ -516,10 +518,10 @@ int main(int argc, char** argv) {
               << " ms -> " << putative << std::endl;
   if (!filter_f) {
     destroy_all();
-    std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f is)" << std::endl;
+    std::cout << "geometric filtering with -g " << opt.geometric_model << " is not part of this build (only -g f and -g h are)" << std::endl;
     return EXIT_SUCCESS;
   }
-  // ---- 5. geometric filter (fundamental matrix, AC-RANSAC) on GPU 0
+  // ---- 5. geometric filter (fundamental matrix or homography, AC-RANSAC) on GPU 0
   std::cout << std::endl << " - GEOMETRIC FILTERING - " << std::endl;
   const size_t np = put_counts.size();
   put_offsets.assign(np + 1, 0);
@@ -527,14 +529,14 @@ int main(int argc, char** argv) {
   if (put_matches.empty()) put_matches.assign(2, 0);
   mvgcuda_pair_matches gm;
   const double max_residual_error = 4.0;  // compute_matches.cpp:254
-  if (mvgcuda_geometric_filter(ctxs[0], 'f', max_residual_error, 4096, 1u, (int64_t)np, put_pairs.data(), put_counts.data(), put_offsets.data(),
+  if (mvgcuda_geometric_filter(ctxs[0], geo_model, max_residual_error, 4096, 1u, (int64_t)np, put_pairs.data(), put_counts.data(), put_offsets.data(),
                                put_matches.data(), image_sizes.data(), &gm) != MVGCUDA_OK) {
     std::cerr << "geometric filter: " << mvgcuda_last_error(ctxs[0]) << std::endl;
     destroy_all();
     return EXIT_FAILURE;
   }
   const Clock::time_point t_geo = Clock::now();
-  const std::string geo_path = opt.outdir + "/matches.f.txt";  // compute_matches.cpp:64-66,131-133
+  const std::string geo_path = opt.outdir + (geo_model == 'h' ? "/matches.h.txt" : "/matches.f.txt");  // compute_matches.cpp:99-113
   if (mvgcuda_write_matches(geo_path.c_str(), gm.n_pairs, put_pairs.data(), gm.counts, gm.offsets, gm.matches, 1) != MVGCUDA_OK) {
     std::cerr << "cannot write " << geo_path << std::endl;
     destroy_all();
@@ -542,7 +544,7 @@ int main(int argc, char** argv) {
   }
   long long kept_pairs = 0;
   for (int64_t k = 0; k < gm.n_pairs; ++k) kept_pairs += gm.counts[k] > 0;
-  std::cout << "geometric filter (F, AC-RANSAC, 4096 iterations, " << max_residual_error << " px) " << ms(t_export, t_geo) << " ms (GPU time " << gm.gpu_ms << " ms): "
+  std::cout << "geometric filter (" << (geo_model == 'h' ? "H" : "F") << ", AC-RANSAC, 4096 iterations, " << max_residual_error << " px) " << ms(t_export, t_geo) << " ms (GPU time " << gm.gpu_ms << " ms): "
             << kept_pairs << " of " << np << " pairs kept, " << gm.offsets[gm.n_pairs] << " matches, " << gm.rescanned_queries
             << " rand() values consumed, " << gm.knn_kernel_launches << " models re-evaluated with host roots -> " << geo_path << std::endl;
   destroy_all();

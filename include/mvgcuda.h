@@ -212,7 +212,9 @@ int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* p
  * fewer than 2.5 x 7 inliers come back empty.  On the GPU the control flow, the sample stream (glibc rand(), `seed` = 1 ==
  * the reference's never-seeded default, consumed pair after pair in the given order) and the double-precision arithmetic
  * of the solver are the reference's; see DESIGN.md for what is bit-exact and what is not.
- *   model        'f' (the homography / essential variants are not built)
+ *   model        'f' = GeometricFilter_FMatrix_AC, or 'h' = GeometricFilter_HMatrix_AC (homography_acransac.h:18-62: 4-point
+ *                solver, point-to-point residual, pairs with fewer than 2.5 x 4 inliers dropped; every bit of it is
+ *                reproduced on the device, no host values involved); the essential variant is not built
  *   pairs/counts/offsets/matches   the putative matches, laid out like mvgcuda_pair_matches (e.g. the result of
  *                mvgcuda_match_collection, or an imported matches.putative.txt); pairs in std::map order
  *   image_sizes  [n_images][2] = width, height of every uploaded image (lists.txt columns 2, 3)

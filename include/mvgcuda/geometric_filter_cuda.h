@@ -11,9 +11,9 @@
 //
 // Filter() uploads the feature coordinates, runs the AC-RANSAC of every pair on the GPU (mvgcuda_geometric_filter: the
 // reference's sample stream -- glibc rand(), consumed pair after pair in map order --, control flow and double-precision
-// solver) and inserts the pairs that keep inliers, in the reference's (residual) order.  Only GeometricFilter_FMatrix_AC
-// is accepted (the functor's m_dPrecision / max_iteration members are read); the homography / essential functors have no
-// GPU implementation and are refused at compile time.
+// solver) and inserts the pairs that keep inliers, in the reference's (residual) order.  GeometricFilter_FMatrix_AC and
+// GeometricFilter_HMatrix_AC are accepted (their precision / iteration members are read); the essential functor has no GPU
+// implementation and is refused at compile time.
 #ifndef MVGCUDA_GEOMETRIC_FILTER_CUDA_H_
 #define MVGCUDA_GEOMETRIC_FILTER_CUDA_H_
 
@@ -26,6 +26,7 @@
 #include "mvg/feature/features.h"
 #include "mvg/feature/indexed_match.h"
 #include "mvg/multiview/fundamental_acransac.h"
+#include "mvg/multiview/homography_acransac.h"
 #include "mvg/utils/file_system.h"
 #include "mvgcuda.h"
 
@@ -52,8 +53,9 @@ class ImageCollectionGeometricFilterCuda {
   template <typename GeometricFilterT>
   void Filter(const GeometricFilterT& geometric_filter, PairWiseMatches& map_putatives_matches_pair,
               PairWiseMatches& map_geometric_matches, const std::vector<std::pair<size_t, size_t> >& vec_images_size) const {
-    static_assert(std::is_same<GeometricFilterT, mvg::multiview::GeometricFilter_FMatrix_AC>::value,
-                  "ImageCollectionGeometricFilterCuda: only GeometricFilter_FMatrix_AC runs on the GPU");
+    static_assert(std::is_same<GeometricFilterT, mvg::multiview::GeometricFilter_FMatrix_AC>::value ||
+                      std::is_same<GeometricFilterT, mvg::multiview::GeometricFilter_HMatrix_AC>::value,
+                  "ImageCollectionGeometricFilterCuda: only GeometricFilter_FMatrix_AC and GeometricFilter_HMatrix_AC run on the GPU");
     const int n = (int)map_features.size();
     std::vector<std::vector<float> > xy(n);
     std::vector<const float*> xy_ptr(n, (const float*)NULL);
@@ -87,7 +89,7 @@ class ImageCollectionGeometricFilterCuda {
     // only the coordinates are needed on the device: an arena with the right row counts and no descriptors
     mvgcuda_pair_matches gm;
     if (mvgcuda_stream_begin(ctx, n, rows.data()) != MVGCUDA_OK || !stream_features(ctx, n, rows, xy_ptr) || mvgcuda_stream_end(ctx) != MVGCUDA_OK ||
-        mvgcuda_geometric_filter(ctx, 'f', geometric_filter.m_dPrecision, (int)geometric_filter.max_iteration, seed_, (int64_t)counts.size(),
+        mvgcuda_geometric_filter(ctx, model_of(geometric_filter), geometric_filter.m_dPrecision, iterations_of(geometric_filter), seed_, (int64_t)counts.size(),
                                  pairs.data(), counts.data(), offsets.data(), matches.data(), sizes.data(), &gm) != MVGCUDA_OK) {
       std::cerr << "ImageCollectionGeometricFilterCuda: " << mvgcuda_last_error(ctx) << std::endl;
       mvgcuda_destroy(ctx);
@@ -105,6 +107,10 @@ class ImageCollectionGeometricFilterCuda {
   }
 
  private:
+  static char model_of(const mvg::multiview::GeometricFilter_FMatrix_AC&) { return 'f'; }
+  static char model_of(const mvg::multiview::GeometricFilter_HMatrix_AC&) { return 'h'; }
+  static int iterations_of(const mvg::multiview::GeometricFilter_FMatrix_AC& f) { return (int)f.max_iteration; }
+  static int iterations_of(const mvg::multiview::GeometricFilter_HMatrix_AC& f) { return (int)f.m_stIteration; }
   static bool stream_features(mvgcuda_ctx* ctx, int n, const std::vector<int32_t>& rows, const std::vector<const float*>& xy) {
     std::vector<std::vector<uint8_t> > zeros(n);
     for (int i = 0; i < n; ++i) {

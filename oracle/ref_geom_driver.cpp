@@ -142,37 +142,49 @@ void ref_logc(int n, float* logc_n, float* logc_k) {
 // One pair through the reference's own kernel + ACRANSAC (fundamental_acransac.h:23-47 without the final 2.5 x 7 floor):
 // xI, xJ [n][2] float feature coordinates.  inliers: capacity n.  out[0] = errorMax, out[1] = minNFA, out[2] = rand() calls
 // consumed (counted by re-running the stream).  Returns the number of inliers.
-int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
-                   unsigned seed, int* inliers, double* out) {
+}  // extern "C"
+
+// ACRANSAC on one pair with the kernel a filter functor builds; out = {errorMax, minNFA, rand() values consumed}.
+template <typename KernelType>
+static int run_acransac(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, bool point_to_line, double precision,
+                        int iterations, unsigned seed, int* inliers, double* out) {
   Mat a(2, n), b(2, n);
   for (int i = 0; i < n; ++i) {
     a.col(i) = Vec2f(xI[2 * i], xI[2 * i + 1]).cast<double>();
     b.col(i) = Vec2f(xJ[2 * i], xJ[2 * i + 1]).cast<double>();
   }
-  typedef ACKernelAdaptor<fundamental::SevenPointSolver, fundamental::SimpleError, UnnormalizerT, Mat3> KernelType;
-  KernelType kernel(a, wI, hI, b, wJ, hJ, true);
+  KernelType kernel(a, wI, hI, b, wJ, hJ, point_to_line);
   std::vector<size_t> vec_inliers;
-  Mat3 F;
+  Mat3 M;
   srand(seed);
-  std::pair<double, double> r = ACRANSAC(kernel, vec_inliers, (size_t)iterations, &F, precision);
-  // how far the stream moved: find the position whose next value equals what rand() returns now
+  std::pair<double, double> r = ACRANSAC(kernel, vec_inliers, (size_t)iterations, &M, precision);
+  // how far the stream moved: the position (a multiple of the sample size) whose value is what rand() returns now
   const unsigned next = (unsigned)rand();
   srand(seed);
-  long used = 0;
-  {
-    std::vector<unsigned> probe;
-    // the stream never repeats within 2^31 draws; match a window of 4 to be safe
-    unsigned w1 = (unsigned)rand(), w2 = (unsigned)rand(), w3 = (unsigned)rand();
-    srand(seed);
-    std::vector<unsigned> all((size_t)iterations * 7 + 8);
-    for (size_t i = 0; i < all.size(); ++i) all[i] = (unsigned)rand();
-    (void)w1; (void)w2; (void)w3;
-    used = -1;
-    for (size_t i = 0; i < all.size(); ++i) if (all[i] == next && (i % 7) == 0) { used = (long)i; break; }
-  }
+  const size_t sample = KernelType::MINIMUM_SAMPLES;
+  std::vector<unsigned> all((size_t)iterations * sample + 8);
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (unsigned)rand();
+  long used = -1;
+  for (size_t i = 0; i < all.size(); ++i) if (all[i] == next && (i % sample) == 0) { used = (long)i; break; }
   for (size_t i = 0; i < vec_inliers.size(); ++i) inliers[i] = (int)vec_inliers[i];
   out[0] = r.first; out[1] = r.second; out[2] = (double)used;
   return (int)vec_inliers.size();
+}
+
+extern "C" {
+
+// GeometricFilter_FMatrix_AC::Fit's kernel (fundamental_acransac.h:30-42): point-to-line.
+int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                   unsigned seed, int* inliers, double* out) {
+  typedef ACKernelAdaptor<fundamental::SevenPointSolver, fundamental::SimpleError, UnnormalizerT, Mat3> KernelType;
+  return run_acransac<KernelType>(xI, xJ, n, wI, hI, wJ, hJ, true, precision, iterations, seed, inliers, out);
+}
+
+// GeometricFilter_HMatrix_AC::Fit's kernel (homography_acransac.h:35-46): point-to-point.
+int ref_acransac_h(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                   unsigned seed, int* inliers, double* out) {
+  typedef ACKernelAdaptor<homography::FourPointSolver, homography::AsymmetricError, UnnormalizerI, Mat3> KernelType;
+  return run_acransac<KernelType>(xI, xJ, n, wI, hI, wJ, hJ, false, precision, iterations, seed, inliers, out);
 }
 
 }  // extern "C"

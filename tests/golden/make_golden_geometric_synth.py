@@ -4,9 +4,12 @@ iterations, the reserve logic), long inlier lists (> 256: the global-scratch sor
 by index), tiny pairs (<= 7 matches: nothing drawn from rand(); 8..17: below the 2.5 x 7 floor) and an empty pair --
 filtered by the reference's OWN ImageCollectionGeometricFilter + GeometricFilter_FMatrix_AC
 (oracle/_ref/libmvgref_geom.so, built by oracle/build_ref.sh from /root/reference), glibc rand() stream = srand(1).
+A second collection whose points lie on one slanted plane goes through GeometricFilter_HMatrix_AC the same way.
 
     python tests/golden/make_golden_geometric_synth.py   ->  tests/golden/geo_synth.npz, geo_synth_putative.txt,
-                                                             geo_synth_matches_f.txt, geo_synth_golden.json
+                                                             geo_synth_matches_f.txt, geo_synth_golden.json,
+                                                             geo_synth_h.npz, geo_synth_h_putative.txt,
+                                                             geo_synth_matches_h.txt, geo_synth_h_golden.json
 """
 import ctypes as C
 import hashlib
@@ -27,9 +30,11 @@ def g6(a):
     return np.array([float("%g" % v) for v in np.asarray(a, np.float32).ravel()], np.float32).reshape(np.shape(a))
 
 
-def collection(seed=2024):
+def collection(seed=2024, planar=False):
     rng = np.random.default_rng(seed)
     X = np.stack([rng.uniform(-2.2, 2.2, N_PTS), rng.uniform(-1.6, 1.6, N_PTS), rng.uniform(6, 14, N_PTS)], 1)
+    if planar:  # one slanted plane: every pair of views is related by a homography
+        X[:, 2] = 9.0 + 0.8 * X[:, 0] - 0.5 * X[:, 1]
     feats = []
     for k, (w, h) in enumerate(SIZES):
         th = 0.08 * (k - 3)
@@ -75,15 +80,15 @@ def putatives(rng):
     return out, kinds
 
 
-def main():
+def generate(model, stem, feats, rng):
     import importlib, sys
     sys.path.insert(0, ROOT)
     io = importlib.import_module("3dreconstruction_b200.io")
-    feats, rng = collection()
     put, kinds = putatives(rng)
     text = io.matches_to_text(put)
-    open(os.path.join(GOLD, "geo_synth_putative.txt"), "w").write(text)
-    np.savez_compressed(os.path.join(GOLD, "geo_synth.npz"), sizes=np.array(SIZES, np.int32), **{f"feat_{k}": f for k, f in enumerate(feats)})
+    putative = os.path.join(GOLD, stem + "_putative.txt")
+    open(putative, "w").write(text)
+    np.savez_compressed(os.path.join(GOLD, stem + ".npz"), sizes=np.array(SIZES, np.int32), **{f"feat_{k}": f for k, f in enumerate(feats)})
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmvgref_geom.so"))
     lib.ref_geometric_filter.restype = C.c_int
     lib.ref_geometric_filter.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_char, C.c_double, C.c_uint, C.c_char_p]
@@ -92,15 +97,22 @@ def main():
         for k, f in enumerate(feats):
             io.save_feats(os.path.join(td, f"im{k}.feat"), np.concatenate([f, np.ones((len(f), 2), np.float32)], 1))
         sizes = (C.c_int * (2 * N_IMG))(*[v for wh in SIZES for v in wh])
-        out = os.path.join(GOLD, "geo_synth_matches_f.txt")
-        n = lib.ref_geometric_filter(td.encode(), "\n".join(names).encode(), sizes, os.path.join(GOLD, "geo_synth_putative.txt").encode(), b"f", 4.0, 1, out.encode())
+        out = os.path.join(GOLD, ("geo_synth_matches_%s.txt" % model))
+        n = lib.ref_geometric_filter(td.encode(), "\n".join(names).encode(), sizes, putative.encode(), model.encode(), 4.0, 1, out.encode())
     data = open(out, "rb").read()
     got = io.matches_from_text(data.decode())
     meta = {"seed": 1, "max_residual": 4.0, "iterations": 4096, "pairs_kept": n, "matches": int(sum(len(v) for v in got.values())),
             "sha256": hashlib.sha256(data).hexdigest(), "kinds": kinds,
             "kept": {f"{i},{j}": len(v) for (i, j), v in sorted(got.items())}}
-    json.dump(meta, open(os.path.join(GOLD, "geo_synth_golden.json"), "w"), indent=1, sort_keys=True)
+    json.dump(meta, open(os.path.join(GOLD, stem + "_golden.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))
+
+
+def main():
+    feats, rng = collection()
+    generate("f", "geo_synth", feats, rng)                 # 3-D scene, GeometricFilter_FMatrix_AC
+    feats, rng = collection(seed=2025, planar=True)
+    generate("h", "geo_synth_h", feats, rng)               # planar scene, GeometricFilter_HMatrix_AC
 
 
 if __name__ == "__main__":

@@ -15,7 +15,7 @@ sed 's/std::vector<DistanceType>::const_iterator/typename &/' "$REF/libs/feature
 g++ -std=c++11 -O2 -w -pthread -I"$TMP" -I"$ROOT/include" -I"$REF/libs/base/include" -I"$REF/libs/feature/include" -I"$REF/3rdparty/eigen3" \
     -I"$REF/libs/base/src" -I"$REF/libs/multiview/include" -I"$REF/libs/camera/include" -I"$REF/libs/image/include" \
     "$ROOT/tests/native/test_adaptors.cpp" "$REF/libs/base/src/utils/file_system.cpp" "$REF/libs/base/src/utils/wildcard.cpp" \
-    "$REF/libs/multiview/src/solver_fundamental_kernel.cpp" "$REF/libs/multiview/src/conditioning.cpp" "$REF/libs/base/src/math/numeric.cpp" \
+    "$REF/libs/multiview/src/solver_fundamental_kernel.cpp" "$REF/libs/multiview/src/solver_homography_kernel.cpp" "$REF/libs/multiview/src/conditioning.cpp" "$REF/libs/base/src/math/numeric.cpp" \
     "$REF/libs/camera/src/projection.cpp" \
     -L"$ROOT/3dreconstruction_b200" -lmvgcuda -Wl,-rpath,'$ORIGIN/../../3dreconstruction_b200' -o "$OUT/test_adaptors"
 echo "built $OUT/test_adaptors"

@@ -14,6 +14,8 @@
 extern "C" {
 int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
                    unsigned seed, int* inliers, double* out);
+int ref_acransac_h(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                   unsigned seed, int* inliers, double* out);
 void ref_logc(int n, float* logc_n, float* logc_k);
 }
 using namespace mvgcuda::geo;
@@ -31,7 +33,8 @@ struct HostRange {
 static int candidates(const PairGeo& P, const double* F, std::vector<Cand>& list) {
   list.clear();
   for (int i = 0; i < P.n; ++i) {
-    const double e = epipolar_error(F, P.x1[2 * i], P.x1[2 * i + 1], P.x2[2 * i], P.x2[2 * i + 1]);
+    const double e = P.sample == kSampleH ? homography_error(F, P.x1[2 * i], P.x1[2 * i + 1], P.x2[2 * i], P.x2[2 * i + 1])
+                                          : epipolar_error(F, P.x1[2 * i], P.x1[2 * i + 1], P.x2[2 * i], P.x2[2 * i + 1]);
     if (e <= P.max_threshold) list.push_back(Cand{e, i});
   }
   std::sort(list.begin(), list.end(), cand_less);
@@ -40,8 +43,9 @@ static int candidates(const PairGeo& P, const double* F, std::vector<Cand>& list
 
 struct Result { std::vector<int> inliers; double nfa, err_max; long used; };
 
-static Result run_engine(const std::vector<float>& xI, const std::vector<float>& xJ, int n, int wI, int hI, int wJ, int hJ, double precision,
-                         int iterations, unsigned seed) {
+static Result run_engine(char model, const std::vector<float>& xI, const std::vector<float>& xJ, int n, int wI, int hI, int wJ, int hJ,
+                         double precision, int iterations, unsigned seed) {
+  const int sample = model == 'h' ? kSampleH : kSampleF;
   std::vector<double> x1(2 * n), x2(2 * n);
   const Normalizer N1 = make_normalizer(wI, hI), N2 = make_normalizer(wJ, hJ);
   for (int i = 0; i < n; ++i) {
@@ -50,21 +54,23 @@ static Result run_engine(const std::vector<float>& xI, const std::vector<float>&
   }
   std::vector<float> lcn(n + 1), lck(n + 1);
   make_logc_n(n, lcn.data());
-  make_logc_k(kSampleF, n, lck.data());
+  make_logc_k(sample, n, lck.data());
   PairGeo P;
   P.n = n; P.x1 = x1.data(); P.x2 = x2.data();
   P.max_threshold = precision == ac_inf() ? ac_inf() : precision * N2.d * N2.d;
   const double D = sqrt(wJ * (double)wJ + hJ * (double)hJ), A = wJ * (double)hJ;
-  P.logalpha0 = log10(2.0 * D / A / N2.d);
-  P.loge0 = n > kSampleF ? log10((double)3 * (size_t)(n - kSampleF)) : 0.0;
+  // estimator_acransac_kernel_adaptator.h:53-61: point to line 2 D / A / N2(0,0), point to point pi / A / N2(0,0)^2
+  P.logalpha0 = model == 'h' ? log10(M_PI / A / (N2.d * N2.d)) : log10(2.0 * D / A / N2.d);
+  P.loge0 = n > sample ? log10((double)(model == 'h' ? 1 : 3) * (size_t)(n - sample)) : 0.0;
   P.logc_n = lcn.data(); P.logc_k = lck.data();
+  P.sample = sample; P.mult_error = model == 'h' ? 1.0 : 0.5;
   GlibcRand g;
   glibc_srand(g, seed);
-  std::vector<uint32_t> stream((size_t)iterations * 7 + 16);
+  std::vector<uint32_t> stream((size_t)iterations * sample + 16);
   for (auto& v : stream) v = glibc_rand(g);
 
   AcState S;
-  ac_init(S, n, iterations);
+  ac_init(S, n, iterations, sample);
   std::vector<Iter> res(iterations + 8);
   std::vector<int> vec_index(n);
   for (int i = 0; i < n; ++i) vec_index[i] = i;
@@ -75,14 +81,16 @@ static Result run_engine(const std::vector<float>& xI, const std::vector<float>&
     const int hi = ac_range_end(S);
     for (int it = S.iter; it < hi; ++it) {
       int s[7];
-      random_sample<7>(&stream[(size_t)7 * it], S.n_index, s);
+      if (model == 'h') random_sample<4>(&stream[(size_t)4 * it], S.n_index, s);
+      else random_sample<7>(&stream[(size_t)7 * it], S.n_index, s);
       double a[14], b[14];
-      for (int k = 0; k < 7; ++k) {
+      for (int k = 0; k < sample; ++k) {
         const int id = vec_index[s[k]];
         a[2 * k] = x1[2 * id]; a[2 * k + 1] = x1[2 * id + 1]; b[2 * k] = x2[2 * id]; b[2 * k + 1] = x2[2 * id + 1];
       }
       Iter& R = res[it];
-      R.n_models = seven_point_models(a, b, W, V, R.F);
+      if (model == 'h') { double A[144]; four_point_model(a, b, A, W, V, R.F); R.n_models = 1; }
+      else R.n_models = seven_point_models(a, b, W, V, R.F);
       R.nfa = ac_inf(); R.n_inl = 0; R.model = 0;
       for (int k = 0; k < R.n_models; ++k) {
         const int m = candidates(P, R.F + 9 * k, list);
@@ -101,7 +109,7 @@ static Result run_engine(const std::vector<float>& xI, const std::vector<float>&
     }
   }
   Result out;
-  out.nfa = S.min_nfa; out.err_max = ac_inf(); out.used = 7L * S.iter_num;
+  out.nfa = S.min_nfa; out.err_max = ac_inf(); out.used = (long)sample * S.iter_num;
   if (S.min_nfa < 0.0) {  // ACRANSAC clears the inliers of a non-meaningful model (:240-241); the 2.5 x 7 floor is Fit's
     candidates(P, res[S.best_it].F + 9 * S.best_model, list);
     for (int i = 0; i < S.n_inl; ++i) out.inliers.push_back(list[i].i);
@@ -121,9 +129,10 @@ int main() {
     make_logc_k(7, n, d.data());
     if (std::memcmp(a.data(), c.data(), 4 * (n + 1)) || std::memcmp(b.data(), d.data(), 4 * (n + 1))) { std::printf("logc tables differ at n = %d\n", n); ++bad; }
   }
-  for (int t = 0; t < 60; ++t) {
+  for (int t = 0; t < 120; ++t) {
+    const char model = t < 60 ? 'f' : 'h';
     const int kind = t % 6;
-    int n = kind == 5 ? 5 + t % 4 : 30 + (t * 53) % 400;
+    int n = kind == 5 ? (model == 'h' ? 3 : 5) + t % 4 : 30 + (t * 53) % 400;
     const int wI = 4000, hI = 3000, wJ = kind == 2 ? 1416 : 4000, hJ = kind == 2 ? 1064 : 3000;
     std::uniform_real_distribution<float> ux(0.f, (float)wI), uy(0.f, (float)hI), u01(0.f, 1.f), noise(-1.5f, 1.5f);
     std::vector<float> xI(2 * n), xJ(2 * n);
@@ -133,7 +142,7 @@ int main() {
       const float x = ux(rng), y = uy(rng);
       xI[2 * i] = x; xI[2 * i + 1] = y;
       if (u01(rng) < inlier_share) {
-        const float depth = 4.f + 6.f * u01(rng);
+        const float depth = model == 'h' ? 6.f + 0.0004f * x - 0.0003f * y : 4.f + 6.f * u01(rng);  // H: one slanted plane
         const float fx = 3000.f, cx = wI / 2.f, cy = hI / 2.f;
         const float X = (x - cx) / fx * depth, Y = (y - cy) / fx * depth, Z = depth;
         const float th = 0.05f, Xc = std::cos(th) * X + std::sin(th) * Z - 1.0f, Zc = -std::sin(th) * X + std::cos(th) * Z + 0.2f, Yc = Y + 0.1f;
@@ -148,17 +157,17 @@ int main() {
     const unsigned seed = 1 + t;
     std::vector<int> want(n + 1);
     double o[3];
-    const int nw = ref_acransac_f(xI.data(), xJ.data(), n, wI, hI, wJ, hJ, precision, iterations, seed, want.data(), o);
-    const Result got = run_engine(xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, seed);
+    const int nw = (model == 'h' ? ref_acransac_h : ref_acransac_f)(xI.data(), xJ.data(), n, wI, hI, wJ, hJ, precision, iterations, seed, want.data(), o);
+    const Result got = run_engine(model, xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, seed);
     ++cases;
     meaningful += nw > 0;
     bool ok = nw == (int)got.inliers.size() && std::equal(got.inliers.begin(), got.inliers.end(), want.begin());
-    if (n > kSampleF) ok = ok && std::memcmp(&o[1], &got.nfa, 8) == 0;  // (the reference returns (0, 0) without looking when nData <= 7)
+    if (n > (model == 'h' ? kSampleH : kSampleF)) ok = ok && std::memcmp(&o[1], &got.nfa, 8) == 0;  // (the reference returns (0, 0) without looking when nData <= 7)
     if (nw > 0) ok = ok && std::memcmp(&o[0], &got.err_max, 8) == 0;
     if (o[2] >= 0) ok = ok && (long)o[2] == got.used;
     if (!ok) {
       ++bad;
-      std::printf("case %d kind %d n %d: reference %d inliers nfa %.17g used %.0f | engine %zu inliers nfa %.17g used %ld\n", t, kind, n, nw, o[1], o[2],
+      std::printf("case %d model %c kind %d n %d: reference %d inliers nfa %.17g used %.0f | engine %zu inliers nfa %.17g used %ld\n", t, model, kind, n, nw, o[1], o[2],
                   got.inliers.size(), got.nfa, got.used);
     }
   }

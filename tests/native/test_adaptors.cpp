@@ -25,6 +25,7 @@ using namespace mvg::utils;
 #include "mvg/feature/two_view_matches.h"
 #include "mvg/feature/geometric_filter.h"
 #include "mvg/multiview/fundamental_acransac.h"
+#include "mvg/multiview/homography_acransac.h"
 #include "mvgcuda/array_matcher_cuda.h"
 #include "mvgcuda/geometric_filter_cuda.h"
 #include "mvgcuda/matcher_cuda_all_in_memory.h"
@@ -167,6 +168,19 @@ int main(int argc, char** argv) {
         CHECK(t0.str() == t1.str());
         std::cout << "geometric filter (F, AC-RANSAC): " << g0.size() << " pairs kept, " << t0.str().size() << " bytes, identical="
                   << (t0.str() == t1.str()) << std::endl;
+        PairWiseMatches h0, h1;
+        std::cout.rdbuf(sink.rdbuf());
+        srand(1);
+        ref_filter.Filter(mvg::multiview::GeometricFilter_HMatrix_AC(4.0), m0, h0, sizes);
+        std::cout.rdbuf(old);
+        gpu_filter.Filter(mvg::multiview::GeometricFilter_HMatrix_AC(4.0), m1, h1, sizes);
+        std::ostringstream u0, u1;
+        PairedIndexedMatchToStream(h0, u0);
+        PairedIndexedMatchToStream(h1, u1);
+        CHECK(h0.size() == h1.size());
+        CHECK(u0.str() == u1.str());
+        std::cout << "geometric filter (H, AC-RANSAC): " << h0.size() << " pairs kept, " << u0.str().size() << " bytes, identical="
+                  << (u0.str() == u1.str()) << std::endl;
       }
     }
   }

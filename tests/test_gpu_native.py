@@ -56,6 +56,10 @@ def test_compute_matches_geometric_stage_golden(pkg, et, tmp_path):
         assert (tmp_path / "matches.putative.txt").read_bytes() == open(os.path.join(GOLDEN, "et_putative_r0.6.txt"), "rb").read()
         assert (tmp_path / "matches.f.txt").read_bytes() == want_f
         os.remove(tmp_path / "matches.f.txt")
-    # the other models stop after the putative stage
-    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "h"], capture_output=True, text=True, timeout=60)
-    assert out.returncode == 0 and "only -g f" in out.stdout and not (tmp_path / "matches.f.txt").exists()
+    # -g h on the imported putatives: GeometricFilter_HMatrix_AC
+    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "h"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert (tmp_path / "matches.h.txt").read_bytes() == open(os.path.join(GOLDEN, "et_matches_h.txt"), "rb").read()
+    # the essential model (the reference's default, needs K.txt) stops after the putative stage
+    out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "e"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "only -g f and -g h" in out.stdout and not (tmp_path / "matches.e.txt").exists()
