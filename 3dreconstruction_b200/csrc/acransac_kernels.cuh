@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "acransac_engine.cuh"
+#include "stdsort_restated.cuh"
 
 namespace mvgcuda {
 namespace geo {
@@ -153,6 +154,12 @@ struct WarpScratch {
 // Candidates of one model: residual of every point, those <= max_threshold kept in index order (ordered compaction), then
 // sorted by (residual, index) == the head of std::sort(vec_residuals) (estimator_acransac.h:176-181).  Returns their number
 // m; e / idx point to the sorted list (shared memory when m <= kListCap, else the warp's global scratch).
+// one copy of the sequential sort per kernel image (it is inlined nowhere: the path is rare and long)
+__device__ __noinline__ int nan_order_scan(double* ge, int* gi, int n, int sample, double max_threshold) {
+  libstdcxx_sort(ge, gi, n);
+  return nfa_scan_end(ge, n, sample, max_threshold);
+}
+
 __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* F, WarpScratch& ws,
                                                      double* ge, int* gi, int lane, double*& e_out, int*& i_out) {
   double f[9];
@@ -164,6 +171,7 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
   double* le = ws.le;
   int* li = ws.li;
   int cap = kListCap;
+  unsigned any_nan = 0u;
   for (int pass = 0; pass < 2; ++pass) {
     m = 0;
     for (int base = 0; base < P.n; base += 32) {
@@ -175,6 +183,7 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
         e = B.model ? homography_error(f, a.x, a.y, b.x, b.y) : epipolar_error(f, a.x, a.y, b.x, b.y);
         keep = e <= P.max_threshold;
       }
+      any_nan |= __ballot_sync(0xffffffffu, e != e);
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
       if (keep) {
         const int slot = m + __popc(mask & ((1u << lane) - 1u));
@@ -182,8 +191,25 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
       }
       m += __popc(mask);
     }
-    if (m <= cap) break;
+    if (any_nan || m <= cap) break;
     le = ge; li = gi; cap = B.n_cap;  // a long list: once more, into global scratch
+  }
+  if (any_nan) {
+    // A residual is NaN (0 / 0 under a degenerate model): the reference's std::sort over ALL residuals has no strict weak
+    // ordering to work with and its result is defined by its steps only -- repeat them (stdsort_restated.cuh), then take
+    // what bestNFA's scan reaches.  Rare (degenerate samples over exactly collinear / coincident points): one lane.
+    for (int i = lane; i < P.n; i += 32) {
+      const double2 a = x1[i], b = x2[i];
+      ge[i] = B.model ? homography_error(f, a.x, a.y, b.x, b.y) : epipolar_error(f, a.x, a.y, b.x, b.y);
+      gi[i] = i;
+    }
+    __syncwarp();
+    int m_scan = 0;
+    if (lane == 0) m_scan = nan_order_scan(ge, gi, P.n, B.sample, P.max_threshold);
+    m_scan = __shfl_sync(0xffffffffu, m_scan, 0);
+    __syncwarp();
+    e_out = ge; i_out = gi;
+    return m_scan;
   }
   e_out = le; i_out = li;
   if (m < 2) { __syncwarp(); return m; }
@@ -569,6 +595,27 @@ __global__ void geo_selftest_kernel(int n, const double* __restrict__ x1 /*[n][1
   const double e = epipolar_error(f, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
   err[t] = e;
   nfa[t] = nfa_term(-1.25, 2.5, 0.5, e, 8 + (t & 63), kSampleF, 3.5f, 1.25f);
+}
+
+// The homography path exactly as geo_eval_kernel runs it (lane 0: action matrix + QR preconditioner, the warp: Jacobi
+// sweeps), one warp per case: H of a 4-point sample and the transfer error of a probe point under it.
+__global__ void __launch_bounds__(32)
+geo_selftest_h_kernel(int n, const double* __restrict__ x1 /*[n][8]*/, const double* __restrict__ x2, const double* __restrict__ probe /*[n][4]*/,
+                      double* __restrict__ H /*[n][9]*/, double* __restrict__ err) {
+  __shared__ WarpScratch ws;
+  const int t = blockIdx.x, lane = threadIdx.x;
+  if (t >= n) return;
+  if (lane == 0) {
+    double a[2 * kSampleH], b[2 * kSampleH];
+    for (int k = 0; k < 2 * kSampleH; ++k) { a[k] = x1[8 * t + k]; b[k] = x2[8 * t + k]; }
+    four_point_qr(a, b, ws.le, ws.W, ws.V);
+  }
+  __syncwarp();
+  jacobi_svd9_sweeps_warp(ws.W, ws.V, lane);
+  if (lane == 0) {
+    for (int q = 0; q < 9; ++q) { ws.F[q] = ws.V[q + 9 * 8]; H[9 * t + q] = ws.F[q]; }
+    err[t] = homography_error(ws.F, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
+  }
 }
 
 }  // namespace geo

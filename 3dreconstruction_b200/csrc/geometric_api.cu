@@ -461,6 +461,34 @@ extern "C" int mvgcuda_geo_selftest(mvgcuda_ctx* ctx, int n, const double* x1, c
   return MVGCUDA_ERR_NOMEM;
 }
 
+extern "C" int mvgcuda_geo_selftest_h(mvgcuda_ctx* ctx, int n, const double* x1, const double* x2, const double* probe, double* H, double* err) try {
+  if (!ctx || n < 1 || !x1 || !x2 || !probe || !H || !err) return MVGCUDA_ERR_INVALID;
+  const CtxView V = ctx_view(ctx);
+  GEO_CHECK(ctx, cudaSetDevice(V.device));
+  DevBuf<double> d_x1, d_x2, d_p, d_H, d_e;
+  auto cleanup = [&]() { d_x1.release(); d_x2.release(); d_p.release(); d_H.release(); d_e.release(); };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = d_x1.reserve((size_t)n * 8);
+  if (e == cudaSuccess) e = d_x2.reserve((size_t)n * 8);
+  if (e == cudaSuccess) e = d_p.reserve((size_t)n * 4);
+  if (e == cudaSuccess) e = d_H.reserve((size_t)n * 9);
+  if (e == cudaSuccess) e = d_e.reserve(n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x1.p, x1, (size_t)n * 8 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x2.p, x2, (size_t)n * 8 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_p.p, probe, (size_t)n * 4 * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    geo_selftest_h_kernel<<<n, 32>>>(n, d_x1.p, d_x2.p, d_p.p, d_H.p, d_e.p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(H, d_H.p, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(err, d_e.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cleanup();
+  GEO_CHECK(ctx, e);
+  return MVGCUDA_OK;
+} catch (...) {
+  return MVGCUDA_ERR_NOMEM;
+}
+
 // Write n_pairs match lists in the reference's text format, pairs with no match omitted == PairedIndexedMatchToStream over a
 // PairWiseMatches map that only holds non-empty entries (geometric_filter.h:85-98, indexed_match_utils.h:22-38).  `pairs`
 // must be in lexicographic (i, j) order (std::map iteration order).

@@ -94,6 +94,7 @@ ABI: Dict[str, Tuple[object, list]] = {
     "mvgcuda_geometric_filter": (C.c_int, [_ctx, C.c_char, C.c_double, C.c_int, C.c_uint, C.c_int64, _i32p, _i32p, C.POINTER(C.c_int64), _i32p,
                                            _i32p, C.POINTER(_PairMatches)]),
     "mvgcuda_geo_selftest": (C.c_int, [_ctx, C.c_int] + [C.POINTER(C.c_double)] * 4 + [_i32p] + [C.POINTER(C.c_double)] * 2),
+    "mvgcuda_geo_selftest_h": (C.c_int, [_ctx, C.c_int] + [C.POINTER(C.c_double)] * 5),
     "mvgcuda_write_matches": (C.c_int, [C.c_char_p, C.c_int64, _i32p, _i32p, C.POINTER(C.c_int64), _i32p, C.c_int]),
     "mvgcuda_get_device_info": (C.c_int, [_ctx, C.POINTER(_DeviceInfo)]),
     "mvgcuda_probe_i8_peak": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), _f32p]),
@@ -387,6 +388,18 @@ class Context:
         res = self._collect(pairs, pm)
         res.timing["rand_consumed"] = res.timing.pop("rescanned_queries")
         return res
+
+    def geo_selftest_h(self, x1: np.ndarray, x2: np.ndarray, probe: np.ndarray):
+        """Device bits of the homography path: (H [n][9], transfer error [n])."""
+        x1 = np.ascontiguousarray(x1, np.float64).reshape(-1, 8)
+        x2 = np.ascontiguousarray(x2, np.float64).reshape(-1, 8)
+        probe = np.ascontiguousarray(probe, np.float64).reshape(-1, 4)
+        n = len(x1)
+        H = np.zeros((n, 9)); err = np.zeros(n)
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.mvgcuda_geo_selftest_h(self._h, n, x1.ctypes.data_as(dp), x2.ctypes.data_as(dp), probe.ctypes.data_as(dp),
+                                                     H.ctypes.data_as(dp), err.ctypes.data_as(dp)), "mvgcuda_geo_selftest_h")
+        return H, err
 
     def geo_selftest(self, x1: np.ndarray, x2: np.ndarray, probe: np.ndarray):
         """Device bits of the solver core: (F [n][27], n_models [n], residual [n], nfa term [n])."""

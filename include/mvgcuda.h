@@ -238,6 +238,9 @@ int mvgcuda_write_matches(const char* path, int64_t n_pairs, const int32_t* pair
  * model; nfa = one NFA term on that residual.  Lets the tests compare device bits with the reference's. */
 int mvgcuda_geo_selftest(mvgcuda_ctx* ctx, int n, const double* x1, const double* x2, const double* probe, double* F,
                          int32_t* n_models, double* err, double* nfa);
+/* The homography path as the filter runs it (one warp per case): x1/x2 [n][4][2] -> H [n][9] (row-major, unnormalised
+ * null vector of the action matrix); probe [n][4] -> AsymmetricError under it. */
+int mvgcuda_geo_selftest_h(mvgcuda_ctx* ctx, int n, const double* x1, const double* x2, const double* probe, double* H, double* err);
 
 typedef struct mvgcuda_device_info {
   char name[128];

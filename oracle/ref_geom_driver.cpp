@@ -124,6 +124,20 @@ void ref_rand(unsigned seed, int n, unsigned* out) {
   for (int i = 0; i < n; ++i) out[i] = (unsigned)rand();
 }
 
+// How many values the process-wide rand() stream has yielded since srand(seed): the next four values are drawn and
+// located in a regenerated stream (the state is left re-seeded -- call this after a run, not inside one).  -1: beyond limit.
+long ref_rand_position(unsigned seed, long limit) {
+  unsigned w[4];
+  for (int i = 0; i < 4; ++i) w[i] = (unsigned)rand();
+  srand(seed);
+  unsigned a = (unsigned)rand(), b = (unsigned)rand(), c = (unsigned)rand(), d = (unsigned)rand();
+  for (long pos = 0; pos <= limit; ++pos) {
+    if (a == w[0] && b == w[1] && c == w[2] && d == w[3]) return pos;
+    a = b; b = c; c = d; d = (unsigned)rand();
+  }
+  return -1;
+}
+
 void ref_random_sample7(unsigned seed, int skip, int n, int* out) {
   srand(seed);
   for (int i = 0; i < skip; ++i) rand();
@@ -147,7 +161,7 @@ void ref_logc(int n, float* logc_n, float* logc_k) {
 // ACRANSAC on one pair with the kernel a filter functor builds; out = {errorMax, minNFA, rand() values consumed}.
 template <typename KernelType>
 static int run_acransac(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, bool point_to_line, double precision,
-                        int iterations, unsigned seed, int* inliers, double* out) {
+                        int iterations, unsigned seed, int* inliers, double* out, long skip = 0, bool verbose = false) {
   Mat a(2, n), b(2, n);
   for (int i = 0; i < n; ++i) {
     a.col(i) = Vec2f(xI[2 * i], xI[2 * i + 1]).cast<double>();
@@ -157,10 +171,12 @@ static int run_acransac(const float* xI, const float* xJ, int n, int wI, int hI,
   std::vector<size_t> vec_inliers;
   Mat3 M;
   srand(seed);
-  std::pair<double, double> r = ACRANSAC(kernel, vec_inliers, (size_t)iterations, &M, precision);
+  for (long i = 0; i < skip; ++i) rand();  // the pair starts where the pairs before it left the process-wide stream
+  std::pair<double, double> r = ACRANSAC(kernel, vec_inliers, (size_t)iterations, &M, precision, verbose);
   // how far the stream moved: the position (a multiple of the sample size) whose value is what rand() returns now
   const unsigned next = (unsigned)rand();
   srand(seed);
+  for (long i = 0; i < skip; ++i) rand();
   const size_t sample = KernelType::MINIMUM_SAMPLES;
   std::vector<unsigned> all((size_t)iterations * sample + 8);
   for (size_t i = 0; i < all.size(); ++i) all[i] = (unsigned)rand();
@@ -178,6 +194,15 @@ int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int 
                    unsigned seed, int* inliers, double* out) {
   typedef ACKernelAdaptor<fundamental::SevenPointSolver, fundamental::SimpleError, UnnormalizerT, Mat3> KernelType;
   return run_acransac<KernelType>(xI, xJ, n, wI, hI, wJ, hJ, true, precision, iterations, seed, inliers, out);
+}
+
+// The same with the stream advanced by `skip` values first (a pair in the middle of a collection); model 'f' / 'h'.
+int ref_acransac_at(char model, const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                    unsigned seed, long skip, int verbose, int* inliers, double* out) {
+  typedef ACKernelAdaptor<fundamental::SevenPointSolver, fundamental::SimpleError, UnnormalizerT, Mat3> KernelF;
+  typedef ACKernelAdaptor<homography::FourPointSolver, homography::AsymmetricError, UnnormalizerI, Mat3> KernelH;
+  if (model == 'h') return run_acransac<KernelH>(xI, xJ, n, wI, hI, wJ, hJ, false, precision, iterations, seed, inliers, out, skip, verbose != 0);
+  return run_acransac<KernelF>(xI, xJ, n, wI, hI, wJ, hJ, true, precision, iterations, seed, inliers, out, skip, verbose != 0);
 }
 
 // GeometricFilter_HMatrix_AC::Fit's kernel (homography_acransac.h:35-46): point-to-point.

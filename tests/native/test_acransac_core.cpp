@@ -8,7 +8,11 @@
 #include <random>
 #include <vector>
 
+#include <algorithm>
+#include <cmath>
+#include <utility>
 #include "../../3dreconstruction_b200/csrc/acransac_core.cuh"
+#include "../../3dreconstruction_b200/csrc/stdsort_restated.cuh"
 
 extern "C" {
 int ref_seven_point(const double* x1, const double* x2, double* F);
@@ -114,6 +118,60 @@ int main() {
     }
     std::printf("four-point: %ld coefficients compared, %ld differ in bits, residual mismatches %ld\n", coeffs, bits_diff, err_diff);
     if (bits_diff || err_diff) ++bad;
+  }
+  // 7. std::sort restated (csrc/stdsort_restated.cuh) against THIS toolchain's std::sort on (residual, index) arrays with
+  //    NaNs in them -- no strict weak ordering, the result is whatever the introsort steps leave.  The real sort runs inside
+  //    a padded buffer whose guard entries stop an unguarded scan that leaves the range (cases where the restatement
+  //    reports it left the array are not compared: the reference would have read foreign memory there).
+  {
+    typedef std::pair<double, size_t> EI;
+    std::uniform_real_distribution<double> u(0.0, 1.0);
+    long cases = 0, differ = 0, left = 0, with_nan = 0, heap_path = 0;
+    for (int t = 0; t < 6000; ++t) {
+      const int n = t < 200 ? 1 + t % 40 : 17 + (t * 131) % 3000;
+      const int kind = t % 6;
+      std::vector<double> e(n);
+      for (int i = 0; i < n; ++i) e[i] = kind == 4 ? std::floor(8 * u(rng)) : u(rng);   // kind 4: many equal residuals
+      const double share = kind == 0 ? 0.0 : kind == 1 ? 0.02 : kind == 2 ? 0.2 : kind == 3 ? 0.7 : 0.1;
+      int nn = 0;
+      for (int i = 0; i < n; ++i) if (u(rng) < share) { e[i] = std::nan(""); ++nn; }
+      if (kind == 5) for (int i = 0; i < n; ++i) if (u(rng) < 0.1) e[i] = INFINITY;
+      const int pad = 64;
+      std::vector<EI> buf(n + 2 * pad);
+      for (int i = 0; i < pad; ++i) { buf[i] = EI(-INFINITY, 0); buf[pad + n + i] = EI(INFINITY, (size_t)-1); }
+      for (int i = 0; i < n; ++i) buf[pad + i] = EI(e[i], (size_t)i);
+      std::sort(buf.begin() + pad, buf.begin() + pad + n);
+      std::vector<double> ge(e);
+      std::vector<int> gi(n);
+      for (int i = 0; i < n; ++i) gi[i] = i;
+      const int la = libstdcxx_sort(ge.data(), gi.data(), n);
+      ++cases; with_nan += nn > 0;
+      if (la) { ++left; continue; }
+      bool same = true;
+      for (int i = 0; i < n && same; ++i) same = (int)buf[pad + i].second == gi[i] && same_bits(buf[pad + i].first, ge[i]);
+      if (!same) { if (differ < 5) std::printf("std::sort restatement differs: case %d n %d kind %d NaNs %d\n", t, n, kind, nn); ++differ; }
+    }
+    // adversarial for the depth limit (heap sort branch): organ-pipe / median-of-3 killer-ish inputs
+    for (int t = 0; t < 40; ++t) {
+      const int n = 200 + 97 * t;
+      std::vector<double> e(n);
+      for (int i = 0; i < n; ++i) e[i] = (t & 1) ? (double)((i * 7919) % 13) : (i < n / 2 ? i : n - i);
+      if (t % 4 >= 2) for (int i = 0; i < n; i += 9) e[i] = std::nan("");
+      std::vector<EI> buf(n + 128);
+      for (int i = 0; i < 64; ++i) { buf[i] = EI(-INFINITY, 0); buf[64 + n + i] = EI(INFINITY, (size_t)-1); }
+      for (int i = 0; i < n; ++i) buf[64 + i] = EI(e[i], (size_t)i);
+      std::sort(buf.begin() + 64, buf.begin() + 64 + n);
+      std::vector<int> gi(n);
+      for (int i = 0; i < n; ++i) gi[i] = i;
+      const int la = libstdcxx_sort(e.data(), gi.data(), n);
+      ++cases; ++heap_path;
+      if (la) { ++left; continue; }
+      bool same = true;
+      for (int i = 0; i < n && same; ++i) same = (int)buf[64 + i].second == gi[i];
+      if (!same) { ++differ; std::printf("std::sort restatement differs on structured case %d\n", t); }
+    }
+    std::printf("std::sort restated: %ld arrays (%ld with NaNs), %ld differ, %ld left the array (not compared)\n", cases, with_nan, differ, left);
+    if (differ) ++bad;
   }
   std::printf(bad ? "ACRANSAC CORE FAILED\n" : "ACRANSAC CORE OK\n");
   return bad ? 1 : 0;

@@ -10,12 +10,15 @@
 #include <vector>
 
 #include "../../3dreconstruction_b200/csrc/acransac_engine.cuh"
+#include "../../3dreconstruction_b200/csrc/stdsort_restated.cuh"
 
 extern "C" {
 int ref_acransac_f(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
                    unsigned seed, int* inliers, double* out);
 int ref_acransac_h(const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
                    unsigned seed, int* inliers, double* out);
+int ref_acransac_at(char model, const float* xI, const float* xJ, int n, int wI, int hI, int wJ, int hJ, double precision, int iterations,
+                    unsigned seed, long skip, int verbose, int* inliers, double* out);
 void ref_logc(int n, float* logc_n, float* logc_k);
 }
 using namespace mvgcuda::geo;
@@ -30,12 +33,30 @@ struct HostRange {
   int model(int i) const { return r[i].model; }
 };
 
+// The candidates of one model as the product builds them (acransac_kernels.cuh: model_candidates_warp): residuals <=
+// max_threshold sorted by (residual, index); with a NaN among the residuals, std::sort of ALL of them restated step by step
+// (stdsort_restated.cuh) and the length bestNFA's scan reaches.
+static long g_nan_models = 0;
 static int candidates(const PairGeo& P, const double* F, std::vector<Cand>& list) {
   list.clear();
+  std::vector<double> all(P.n);
+  bool any_nan = false;
   for (int i = 0; i < P.n; ++i) {
     const double e = P.sample == kSampleH ? homography_error(F, P.x1[2 * i], P.x1[2 * i + 1], P.x2[2 * i], P.x2[2 * i + 1])
                                           : epipolar_error(F, P.x1[2 * i], P.x1[2 * i + 1], P.x2[2 * i], P.x2[2 * i + 1]);
+    all[i] = e;
+    any_nan = any_nan || e != e;
     if (e <= P.max_threshold) list.push_back(Cand{e, i});
+  }
+  if (any_nan) {
+    ++g_nan_models;
+    std::vector<int> idx(P.n);
+    for (int i = 0; i < P.n; ++i) idx[i] = i;
+    libstdcxx_sort(all.data(), idx.data(), P.n);
+    const int m = nfa_scan_end(all.data(), P.n, P.sample, P.max_threshold);
+    list.resize(m);
+    for (int i = 0; i < m; ++i) list[i] = Cand{all[i], idx[i]};
+    return m;
   }
   std::sort(list.begin(), list.end(), cand_less);
   return (int)list.size();
@@ -44,7 +65,7 @@ static int candidates(const PairGeo& P, const double* F, std::vector<Cand>& list
 struct Result { std::vector<int> inliers; double nfa, err_max; long used; };
 
 static Result run_engine(char model, const std::vector<float>& xI, const std::vector<float>& xJ, int n, int wI, int hI, int wJ, int hJ,
-                         double precision, int iterations, unsigned seed) {
+                         double precision, int iterations, unsigned seed, long skip = 0, bool verbose = false) {
   const int sample = model == 'h' ? kSampleH : kSampleF;
   std::vector<double> x1(2 * n), x2(2 * n);
   const Normalizer N1 = make_normalizer(wI, hI), N2 = make_normalizer(wJ, hJ);
@@ -67,6 +88,7 @@ static Result run_engine(char model, const std::vector<float>& xI, const std::ve
   GlibcRand g;
   glibc_srand(g, seed);
   std::vector<uint32_t> stream((size_t)iterations * sample + 16);
+  for (long i = 0; i < skip; ++i) glibc_rand(g);
   for (auto& v : stream) v = glibc_rand(g);
 
   AcState S;
@@ -101,6 +123,7 @@ static Result run_engine(char model, const std::vector<float>& xI, const std::ve
     }
     HostRange HR{res};
     ac_account(S, HR);
+    if (verbose) std::printf("  engine: accounted up to %d of %d, minNFA %.17g (it %d, %d inliers), reserve %d\n", S.iter, S.iter_num, S.min_nfa, S.best_it, S.n_inl, S.reserve);
     if (S.index_it != cur_it || S.index_model != cur_model) {
       cur_it = S.index_it; cur_model = S.index_model;
       candidates(P, res[cur_it].F + 9 * cur_model, list);
@@ -118,7 +141,26 @@ static Result run_engine(char model, const std::vector<float>& xI, const std::ve
   return out;
 }
 
-int main() {
+// Debug aid: one pair from a file written by tests/tools/geo_h_debug.py --dump:  int32 {model, n, wI, hI, wJ, hJ, skip, iterations}, float xI[2n], xJ[2n]
+static int run_file(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return 2;
+  int h[8];
+  if (std::fread(h, 4, 8, f) != 8) return 2;
+  const int n = h[1];
+  std::vector<float> xI(2 * n), xJ(2 * n);
+  if (std::fread(xI.data(), 4, 2 * n, f) != (size_t)2 * n || std::fread(xJ.data(), 4, 2 * n, f) != (size_t)2 * n) return 2;
+  std::fclose(f);
+  std::vector<int> want(n + 1);
+  double o[3];
+  const int nw = ref_acransac_at((char)h[0], xI.data(), xJ.data(), n, h[2], h[3], h[4], h[5], 4.0, h[7], 1, h[6], 1, want.data(), o);
+  const Result got = run_engine((char)h[0], xI, xJ, n, h[2], h[3], h[4], h[5], 4.0, h[7], 1, h[6], true);
+  std::printf("reference: %d inliers, minNFA %.17g, used %.0f | engine: %zu inliers, minNFA %.17g, used %ld\n", nw, o[1], o[2], got.inliers.size(), got.nfa, got.used);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1) return run_file(argv[1]);
   std::mt19937 rng(11);
   int bad = 0, cases = 0, meaningful = 0;
   // log tables
@@ -152,6 +194,14 @@ int main() {
         xJ[2 * i] = u01(rng) * wJ; xJ[2 * i + 1] = u01(rng) * hJ;
       }
     }
+    if (t % 12 == 6 || t % 12 == 8)  // duplicated correspondences: identical residuals (ties go to the lower index), degenerate samples
+      for (int i = 0; i < n / 5; ++i) { const int d = n - 1 - i; xI[2 * d] = xI[2 * i]; xI[2 * d + 1] = xI[2 * i + 1]; xJ[2 * d] = xJ[2 * i]; xJ[2 * d + 1] = xJ[2 * i + 1]; }
+    if (t % 12 == 3 || t % 12 == 9 || t % 12 == 10)  // features clipped to the image border: collinear triples, 0 / 0 residuals under degenerate models
+      for (int i = 0; i < n; ++i) {
+        if (i % 5 == 0) xI[2 * i] = 0.f;
+        if (i % 7 == 0) xJ[2 * i + 1] = 0.f;
+        if (i % 11 == 0) { xI[2 * i] = 0.f; xI[2 * i + 1] = 0.f; }
+      }
     const double precision = kind == 4 ? ac_inf() : 4.0;
     const int iterations = t % 7 == 3 ? 1024 : 4096;
     const unsigned seed = 1 + t;
@@ -171,6 +221,7 @@ int main() {
                   got.inliers.size(), got.nfa, got.used);
     }
   }
+  std::printf("%ld models had NaN residuals (std::sort restated step by step)\n", g_nan_models);
   std::printf("%d pairs (%d with a meaningful model): %s\n", cases, meaningful, bad ? "MISMATCH" : "inliers, order, minNFA, errorMax and rand() consumption identical");
   std::printf(bad ? "ACRANSAC ENGINE FAILED\n" : "ACRANSAC ENGINE OK\n");
   return bad ? 1 : 0;

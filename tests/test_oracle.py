@@ -325,11 +325,15 @@ def _native(name, tmp_path):
 
 def test_acransac_core_bit_exact_vs_reference(tmp_path):
     """csrc/acransac_core.cuh compiled for the host: glibc rand(), RandomSample, NormalizePoints, the 7-point solver
-    (Eigen 3.2.2 JacobiSVD restated) and the residual, bit for bit against the reference's own classes."""
+    (Eigen 3.2.2 JacobiSVD restated), the 4-point homography solver (column-pivoting QR preconditioner restated) and the
+    residuals, bit for bit against the reference's own classes; csrc/stdsort_restated.cuh against this toolchain's
+    std::sort on (residual, index) arrays WITH NaNs (what ACRANSAC's sort meets under a degenerate model)."""
     assert "ACRANSAC CORE OK" in _native("test_acransac_core", tmp_path)
 
 
 def test_acransac_engine_vs_reference(tmp_path):
     """csrc/acransac_engine.cuh (ranges of iterations evaluated speculatively, accounted for in order) against the
-    reference's sequential ACRANSAC: inliers in order, minNFA / errorMax bits, rand() consumption."""
+    reference's sequential ACRANSAC for both models (7-point F, 4-point H; 120 pairs): inliers in order, minNFA / errorMax
+    bits, rand() consumption -- incl. duplicated correspondences and border-clipped (collinear) points whose degenerate
+    models give NaN residuals."""
     assert "ACRANSAC ENGINE OK" in _native("test_acransac_engine", tmp_path)
