@@ -160,7 +160,7 @@ __device__ __noinline__ int nan_order_scan(double* ge, int* gi, int n, int sampl
   return nfa_scan_end(ge, n, sample, max_threshold);
 }
 
-__device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* F, WarpScratch& ws,
+__device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* F, double* list_e, int* list_i,
                                                      double* ge, int* gi, int lane, double*& e_out, int*& i_out) {
   double f[9];
 #pragma unroll
@@ -168,8 +168,8 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
   const double2* x1 = B.x1 + P.m_off;
   const double2* x2 = B.x2 + P.m_off;
   int m = 0;
-  double* le = ws.le;
-  int* li = ws.li;
+  double* le = list_e;
+  int* li = list_i;
   int cap = kListCap;
   unsigned any_nan = 0u;
   for (int pass = 0; pass < 2; ++pass) {
@@ -252,80 +252,16 @@ __device__ __forceinline__ void best_nfa_warp(const GeoBatchDev& B, const GeoPai
   k_best = v < ac_inf() ? kb : B.sample;
 }
 
-// jacobi_svd9_v (acransac_core.cuh) with the warp cooperating: the 2x2 step is computed by every lane (same inputs from
-// shared memory, same bits), lanes 0-8 then rotate one element pair of the two rows / columns of W each and lanes 9-17 one
-// element pair of V's columns.  Per element exactly the scalar version's operations, so V is bit-identical to it.
-__device__ __forceinline__ void jacobi_svd9_sweeps_warp(double* W, double* V, int lane);
-__device__ __forceinline__ void jacobi_svd9_v_warp(double* W, double* V, int lane) {
-  for (int i = lane; i < 81; i += 32) V[i] = (i % 10 == 0) ? 1.0 : 0.0;
-  jacobi_svd9_sweeps_warp(W, V, lane);
-}
-// the sweeps on a work matrix whose V is already initialised (identity, or the QR preconditioner's column permutation)
-__device__ __forceinline__ void jacobi_svd9_sweeps_warp(double* W, double* V, int lane) {
-  const double precision = 2.0 * DBL_EPSILON;
-  const double consider_as_zero = 2.0 * 4.9406564584124654e-324;
-  double scale = 0.0;
-  for (int i = lane; i < 81; i += 32) { const double a = fabs(W[i]); if (a > scale) scale = a; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, scale, o); if (t > scale) scale = t; }
-  if (scale == 0.0) scale = 1.0;
-  const double inv = 1.0 / scale;
-  __syncwarp();
-  for (int i = lane; i < 81; i += 32) W[i] *= inv;
-  __syncwarp();
-  bool finished = false;
-  while (!finished) {
-    finished = true;
-    for (int p = 1; p < 9; ++p) {
-      for (int q = 0; q < p; ++q) {
-        const double wpp = W[p + 9 * p], wqq = W[q + 9 * q], wpq = W[p + 9 * q], wqp = W[q + 9 * p];
-        const double app = fabs(wpp), aqq = fabs(wqq);
-        const double mx = app < aqq ? aqq : app;
-        const double pm = precision * mx;
-        const double threshold = consider_as_zero < pm ? pm : consider_as_zero;
-        const double apq = fabs(wpq), aqp = fabs(wqp);
-        const double off = apq < aqp ? aqp : apq;
-        if (off > threshold) {  // warp-uniform: every lane read the same four values
-          finished = false;
-          Rot jl, jr;
-          real_2x2_jacobi_svd(wpp, wpq, wqp, wqq, jl, jr);
-          __syncwarp();
-          if (lane < 9 && !(jl.c == 1.0 && jl.s == 0.0)) rotate_pair(W[p + 9 * lane], W[q + 9 * lane], jl.c, jl.s);
-          __syncwarp();
-          if (!(jr.c == 1.0 && -jr.s == 0.0)) {
-            if (lane < 9) rotate_pair(W[lane + 9 * p], W[lane + 9 * q], jr.c, -jr.s);
-            else if (lane < 18) rotate_pair(V[(lane - 9) + 9 * p], V[(lane - 9) + 9 * q], jr.c, -jr.s);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-  // singular values = |diagonal|, selection sort in descending order (first maximum wins), stop at an exact zero
-  double sv[9];
-  for (int i = 0; i < 9; ++i) sv[i] = fabs(W[i + 9 * i]);
-  for (int i = 0; i < 9; ++i) {
-    int pos = 0;
-    double best = sv[i];
-    for (int k = 1; k < 9 - i; ++k) if (sv[i + k] > best) { best = sv[i + k]; pos = k; }
-    if (best == 0.0) break;
-    if (pos) {
-      pos += i;
-      const double t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
-      if (lane < 9) { const double u = V[lane + 9 * pos]; V[lane + 9 * pos] = V[lane + 9 * i]; V[lane + 9 * i] = u; }
-    }
-  }
-  __syncwarp();
-}
-
-// All models of one iteration (already in ws.F): best NFA over the models, strict <, in order (estimator_acransac.h:173-217).
-__device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, const GeoPairDev& P, WarpScratch& ws, int nm, double* ge, int* gi, int lane) {
+// All models of one iteration (F: nm x 9 in shared memory): best NFA over the models, strict <, in order
+// (estimator_acransac.h:173-217).  list_e / list_i: the warp's kListCap-entry candidate list in shared memory.
+__device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, const GeoPairDev& P, const double* F, double* list_e, int* list_i, int nm,
+                                                        double* ge, int* gi, int lane) {
   double best = ac_inf();
   int best_k = 0, best_model = 0;
   for (int k = 0; k < nm; ++k) {
     double* e;
     int* idx;
-    const int m = model_candidates_warp(B, P, ws.F + 9 * k, ws, ge, gi, lane, e, idx);
+    const int m = model_candidates_warp(B, P, F + 9 * k, list_e, list_i, ge, gi, lane, e, idx);
     if (m > B.sample) {
       double v;
       int kb;
@@ -340,12 +276,101 @@ __device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, co
 }
 
 // ------------------------------------------------------------------------------------------ evaluation of ranges
-// One warp per iteration of [round.lo, round.hi) of every slot in the list, with the slot's sampling set
-// vec_index[0 .. n_index) (estimator_acransac.h:166-218).
-constexpr int kEvalWarps = 8;
+// A warp takes kEvalGroup consecutive iterations of [round.lo, round.hi) of a slot (estimator_acransac.h:166-218).
+//   solve:     the Jacobi SVD is a chain of ~250 dependent 2x2 steps (six fp64 divisions and three square roots each) in
+//              which nine lanes at most have element pairs to rotate -- the fp64 pipe, which a warp instruction occupies
+//              whatever its active lanes, is what a wave of evaluations runs out of.  So THREE iterations are solved side
+//              by side, lanes 10 g .. 10 g + 8 on the matrices of iteration g: one instruction stream, every lane computes
+//              the 2x2 step of its own group, a step is skipped only when no group needs it (a converged matrix asks for
+//              nothing more, exactly as its own loop would have ended).  Per element exactly the scalar operations.
+//   evaluate:  the models of the three iterations one after the other, the whole warp on the residuals of each.
+constexpr int kEvalWarps = 4;
+constexpr int kEvalGroup = 3;
+constexpr int kGroupLanes = 10;
+struct SolveScratch {
+  double W[81], V[81], F[27];
+  int n_models, pad;
+};
+struct EvalScratch {
+  SolveScratch s[kEvalGroup];
+  union {
+    struct { double le[kListCap]; int li[kListCap]; } list;
+    double A[kEvalGroup][144];   // homography: the 16 x 9 action matrices while the QR preconditioner runs (before any list)
+  } u;
+  double colmax[kEvalGroup][9];
+};
+
+// jacobi_svd9_sweeps (acransac_core.cuh) on kEvalGroup work matrices at once; V already initialised.
+__device__ __forceinline__ void jacobi_svd9_sweeps_groups(EvalScratch& es, int lane) {
+  const double precision = 2.0 * DBL_EPSILON;
+  const double consider_as_zero = 2.0 * 4.9406564584124654e-324;
+  const int g = lane / kGroupLanes;              // 3: lanes 30, 31 have no group
+  const int gl = lane - g * kGroupLanes;
+  const bool member = g < kEvalGroup;
+  const bool worker = member && gl < 9;
+  double* W = es.s[member ? g : 0].W;
+  double* V = es.s[member ? g : 0].V;
+  if (worker) {
+    double m = 0.0;
+    for (int r = 0; r < 9; ++r) { const double a = fabs(W[r + 9 * gl]); if (a > m) m = a; }
+    es.colmax[g][gl] = m;
+  }
+  __syncwarp();
+  double scale = 0.0;
+  if (member) for (int c = 0; c < 9; ++c) { const double t = es.colmax[g][c]; if (t > scale) scale = t; }
+  if (scale == 0.0) scale = 1.0;
+  const double inv = 1.0 / scale;
+  if (worker) for (int r = 0; r < 9; ++r) W[r + 9 * gl] *= inv;
+  __syncwarp();
+  bool again = true;
+  while (again) {
+    bool rotated = false;
+    for (int p = 1; p < 9; ++p) {
+      for (int q = 0; q < p; ++q) {
+        const double wpp = W[p + 9 * p], wqq = W[q + 9 * q], wpq = W[p + 9 * q], wqp = W[q + 9 * p];
+        const double app = fabs(wpp), aqq = fabs(wqq);
+        const double mx = app < aqq ? aqq : app;
+        const double pm = precision * mx;
+        const double threshold = consider_as_zero < pm ? pm : consider_as_zero;
+        const double apq = fabs(wpq), aqp = fabs(wqp);
+        const double off = apq < aqp ? aqp : apq;
+        const bool need = member && off > threshold;   // uniform within a group
+        if (!__any_sync(0xffffffffu, need)) continue;
+        rotated = rotated || need;
+        Rot jl, jr;
+        real_2x2_jacobi_svd(wpp, wpq, wqp, wqq, jl, jr);
+        __syncwarp();
+        if (need && worker && !(jl.c == 1.0 && jl.s == 0.0)) rotate_pair(W[p + 9 * gl], W[q + 9 * gl], jl.c, jl.s);
+        __syncwarp();
+        if (need && worker && !(jr.c == 1.0 && -jr.s == 0.0)) {
+          rotate_pair(W[gl + 9 * p], W[gl + 9 * q], jr.c, -jr.s);
+          rotate_pair(V[gl + 9 * p], V[gl + 9 * q], jr.c, -jr.s);
+        }
+        __syncwarp();
+      }
+    }
+    again = __any_sync(0xffffffffu, rotated);
+  }
+  // singular values = |diagonal|, selection sort in descending order (first maximum wins), stop at an exact zero
+  double sv[9];
+  for (int i = 0; i < 9; ++i) sv[i] = fabs(W[i + 9 * i]);
+  for (int i = 0; i < 9; ++i) {
+    int pos = 0;
+    double best = sv[i];
+    for (int k = 1; k < 9 - i; ++k) if (sv[i + k] > best) { best = sv[i + k]; pos = k; }
+    if (best == 0.0) break;
+    if (pos) {
+      pos += i;
+      const double t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
+      if (worker) { const double u = V[gl + 9 * pos]; V[gl + 9 * pos] = V[gl + 9 * i]; V[gl + 9 * i] = u; }
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(32 * kEvalWarps)
 geo_eval_kernel(GeoBatchDev B, EvalList L) {
-  __shared__ WarpScratch scratch[kEvalWarps];
+  __shared__ EvalScratch scratch[kEvalWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kEvalWarps + warp;
   int k = 0;
@@ -353,71 +378,88 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   if (gwarp >= L.first_warp[L.n]) return;
   const SlotView V = slot_view(B, L.slot[k]);
   const RoundInfo R = *V.round;
-  const int it = R.lo + (gwarp - L.first_warp[k]);
-  if (it >= R.hi) return;
+  const int it0 = R.lo + kEvalGroup * (gwarp - L.first_warp[k]);
+  if (it0 >= R.hi) return;
   const GeoPairDev P = B.pairs[R.pair];
   const bool identity = V.state->index_it < 0;
-  WarpScratch& ws = scratch[warp];
+  EvalScratch& es = scratch[warp];
   double* ge = B.g_e + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
   int* gi = B.g_i + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
+  const int g = lane / kGroupLanes, gl = lane - g * kGroupLanes;
+  const bool member = g < kEvalGroup;
+  const int it = it0 + g;
+  const bool live = member && it < R.hi;          // the group has an iteration to solve
+  const bool leader = member && gl == 0;
+  SolveScratch& sg = es.s[member ? g : 0];
   const uint32_t* rs = B.stream + (R.offset + static_cast<long long>(B.sample) * it - B.stream_base);
   if (B.model == 0) {
-    if (lane == 0) {
-      uint32_t r[kSampleF];
-      for (int q = 0; q < kSampleF; ++q) r[q] = rs[q];
-      int s[kSampleF];
-      random_sample<kSampleF>(r, R.n_index, s);
-      for (int i = 0; i < 81; ++i) ws.W[i] = 0.0;
-      for (int q = 0; q < kSampleF; ++q) {  // EncodeEpipolarEquation (seven_point_basis)
-        const int id = identity ? s[q] : V.vec_index[s[q]];
-        const double2 a = B.x1[P.m_off + id], b = B.x2[P.m_off + id];
-        ws.W[q + 9 * 0] = b.x * a.x; ws.W[q + 9 * 1] = b.x * a.y; ws.W[q + 9 * 2] = b.x;
-        ws.W[q + 9 * 3] = b.y * a.x; ws.W[q + 9 * 4] = b.y * a.y; ws.W[q + 9 * 5] = b.y;
-        ws.W[q + 9 * 6] = a.x;       ws.W[q + 9 * 7] = a.y;       ws.W[q + 9 * 8] = 1.0;
+    if (member && gl < 9)
+      for (int r = 0; r < 9; ++r) sg.V[r + 9 * gl] = r == gl ? 1.0 : 0.0;
+    if (leader) {
+      for (int i = 0; i < 81; ++i) sg.W[i] = 0.0;   // (an idle group keeps a zero matrix: it never asks for a rotation)
+      if (live) {
+        uint32_t r[kSampleF];
+        for (int q = 0; q < kSampleF; ++q) r[q] = rs[q];
+        int s[kSampleF];
+        random_sample<kSampleF>(r, R.n_index, s);
+        for (int q = 0; q < kSampleF; ++q) {  // EncodeEpipolarEquation (seven_point_basis)
+          const int id = identity ? s[q] : V.vec_index[s[q]];
+          const double2 a = B.x1[P.m_off + id], b = B.x2[P.m_off + id];
+          sg.W[q + 9 * 0] = b.x * a.x; sg.W[q + 9 * 1] = b.x * a.y; sg.W[q + 9 * 2] = b.x;
+          sg.W[q + 9 * 3] = b.y * a.x; sg.W[q + 9 * 4] = b.y * a.y; sg.W[q + 9 * 5] = b.y;
+          sg.W[q + 9 * 6] = a.x;       sg.W[q + 9 * 7] = a.y;       sg.W[q + 9 * 8] = 1.0;
+        }
       }
     }
     __syncwarp();
-    jacobi_svd9_v_warp(ws.W, ws.V, lane);
-    if (lane == 0) {
+    jacobi_svd9_sweeps_groups(es, lane);
+    if (leader && live) {
       double Pc[4], roots[3];
-      cubic_from_null_vectors(ws.V + 9 * 8, ws.V + 9 * 7, Pc);
+      cubic_from_null_vectors(sg.V + 9 * 8, sg.V + 9 * 7, Pc);
       const int nr = solve_cubic(Pc, roots);  // CUDA's acos / cos / pow: approximate in the last bit
-      models_from_roots(ws.V + 9 * 8, ws.V + 9 * 7, roots, nr, ws.F);
-      ws.n_models = nr;
+      models_from_roots(sg.V + 9 * 8, sg.V + 9 * 7, roots, nr, sg.F);
+      sg.n_models = nr;
       double* bs = V.basis + static_cast<size_t>(it) * kBasisDoubles;
-      for (int q = 0; q < 9; ++q) { bs[q] = ws.V[9 * 8 + q]; bs[9 + q] = ws.V[9 * 7 + q]; }
+      for (int q = 0; q < 9; ++q) { bs[q] = sg.V[9 * 8 + q]; bs[9 + q] = sg.V[9 * 7 + q]; }
       for (int q = 0; q < 4; ++q) bs[18 + q] = Pc[q];
       double* out = V.models + static_cast<size_t>(it) * 27;
-      for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
+      for (int q = 0; q < 9 * nr; ++q) out[q] = sg.F[q];
     }
   } else {
     // homography: no transcendental anywhere (QR preconditioner + Jacobi: +, -, *, /, sqrt), so the device model IS the
     // reference's model bit for bit and nothing ever has to be re-evaluated with host values
-    if (lane == 0) {
-      uint32_t r[kSampleH];
-      for (int q = 0; q < kSampleH; ++q) r[q] = rs[q];
-      int s[kSampleH];
-      random_sample<kSampleH>(r, R.n_index, s);
-      double a[2 * kSampleH], b[2 * kSampleH];
-      for (int q = 0; q < kSampleH; ++q) {
-        const int id = identity ? s[q] : V.vec_index[s[q]];
-        const double2 u = B.x1[P.m_off + id], w = B.x2[P.m_off + id];
-        a[2 * q] = u.x; a[2 * q + 1] = u.y; b[2 * q] = w.x; b[2 * q + 1] = w.y;
+    if (leader) {
+      if (live) {
+        uint32_t r[kSampleH];
+        for (int q = 0; q < kSampleH; ++q) r[q] = rs[q];
+        int s[kSampleH];
+        random_sample<kSampleH>(r, R.n_index, s);
+        double a[2 * kSampleH], b[2 * kSampleH];
+        for (int q = 0; q < kSampleH; ++q) {
+          const int id = identity ? s[q] : V.vec_index[s[q]];
+          const double2 u = B.x1[P.m_off + id], w = B.x2[P.m_off + id];
+          a[2 * q] = u.x; a[2 * q + 1] = u.y; b[2 * q] = w.x; b[2 * q + 1] = w.y;
+        }
+        four_point_qr(a, b, es.u.A[g], sg.W, sg.V);
+      } else {
+        for (int i = 0; i < 81; ++i) { sg.W[i] = 0.0; sg.V[i] = 0.0; }
       }
-      four_point_qr(a, b, ws.le /* 144 doubles of scratch: the candidate list is not in use yet */, ws.W, ws.V);
     }
     __syncwarp();
-    jacobi_svd9_sweeps_warp(ws.W, ws.V, lane);
-    if (lane == 0) {
-      for (int q = 0; q < 9; ++q) ws.F[q] = ws.V[q + 9 * 8];
-      ws.n_models = 1;
+    jacobi_svd9_sweeps_groups(es, lane);
+    if (leader && live) {
+      for (int q = 0; q < 9; ++q) sg.F[q] = sg.V[q + 9 * 8];
+      sg.n_models = 1;
       double* out = V.models + static_cast<size_t>(it) * 27;
-      for (int q = 0; q < 9; ++q) out[q] = ws.F[q];
+      for (int q = 0; q < 9; ++q) out[q] = sg.F[q];
     }
   }
   __syncwarp();
-  const IterRes r = evaluate_models_warp(B, P, ws, ws.n_models, ge, gi, lane);
-  if (lane == 0) { V.res[it] = r; V.exact[it] = B.model; }  // a homography model needs no second look
+  for (int q = 0; q < kEvalGroup && it0 + q < R.hi; ++q) {
+    const IterRes r = evaluate_models_warp(B, P, es.s[q].F, es.u.list.le, es.u.list.li, es.s[q].n_models, ge, gi, lane);
+    if (lane == 0) { V.res[it0 + q] = r; V.exact[it0 + q] = B.model; }  // a homography model needs no second look
+    __syncwarp();
+  }
 }
 
 // The same iterations again with the roots the host's C library computed for their cubics: bit-identical to the reference.
@@ -437,7 +479,7 @@ geo_exact_kernel(GeoBatchDev B, ExactList L) {
     for (int q = 0; q < 9 * nr; ++q) out[q] = ws.F[q];
   }
   __syncwarp();
-  const IterRes r = evaluate_models_warp(B, P, ws, nr, V.ge, V.gi, lane);
+  const IterRes r = evaluate_models_warp(B, P, ws.F, ws.le, ws.li, nr, V.ge, V.gi, lane);
   if (lane == 0) { V.res[it] = r; V.exact[it] = 1; }
 }
 
@@ -544,7 +586,7 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
   if (!S.done && (S.index_it != old_it || S.index_model != old_model)) {
     double* e;
     int* idx;
-    model_candidates_warp(B, P, V.models + static_cast<size_t>(S.index_it) * 27 + 9 * S.index_model, ws, V.ge, V.gi, lane, e, idx);
+    model_candidates_warp(B, P, V.models + static_cast<size_t>(S.index_it) * 27 + 9 * S.index_model, ws.le, ws.li, V.ge, V.gi, lane, e, idx);
     for (int q = lane; q < S.n_index; q += 32) V.vec_index[q] = idx[q];
   }
   if (S.done) {
@@ -552,7 +594,7 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
     if (n_final > 0) {
       double* e;
       int* idx;
-      model_candidates_warp(B, P, V.models + static_cast<size_t>(S.best_it) * 27 + 9 * S.best_model, ws, V.ge, V.gi, lane, e, idx);
+      model_candidates_warp(B, P, V.models + static_cast<size_t>(S.best_it) * 27 + 9 * S.best_model, ws.le, ws.li, V.ge, V.gi, lane, e, idx);
       for (int q = lane; q < n_final; q += 32) B.out_idx[P.m_off + q] = idx[q];
     }
     if (lane == 0) { B.out_count[R.pair] = n_final; B.out_iters[R.pair] = S.iter_num; }
@@ -597,24 +639,33 @@ __global__ void geo_selftest_kernel(int n, const double* __restrict__ x1 /*[n][1
   nfa[t] = nfa_term(-1.25, 2.5, 0.5, e, 8 + (t & 63), kSampleF, 3.5f, 1.25f);
 }
 
-// The homography path exactly as geo_eval_kernel runs it (lane 0: action matrix + QR preconditioner, the warp: Jacobi
-// sweeps), one warp per case: H of a 4-point sample and the transfer error of a probe point under it.
+// The homography path exactly as geo_eval_kernel runs it (three cases per warp: the group leaders build the action matrix
+// and run the QR preconditioner, the groups sweep side by side): H of a 4-point sample and the transfer error of a probe
+// point under it.
 __global__ void __launch_bounds__(32)
 geo_selftest_h_kernel(int n, const double* __restrict__ x1 /*[n][8]*/, const double* __restrict__ x2, const double* __restrict__ probe /*[n][4]*/,
                       double* __restrict__ H /*[n][9]*/, double* __restrict__ err) {
-  __shared__ WarpScratch ws;
-  const int t = blockIdx.x, lane = threadIdx.x;
-  if (t >= n) return;
-  if (lane == 0) {
-    double a[2 * kSampleH], b[2 * kSampleH];
-    for (int k = 0; k < 2 * kSampleH; ++k) { a[k] = x1[8 * t + k]; b[k] = x2[8 * t + k]; }
-    four_point_qr(a, b, ws.le, ws.W, ws.V);
+  __shared__ EvalScratch es;
+  const int lane = threadIdx.x;
+  const int g = lane / kGroupLanes, gl = lane - g * kGroupLanes;
+  const bool member = g < kEvalGroup;
+  const int t = blockIdx.x * kEvalGroup + g;
+  const bool live = member && t < n, leader = member && gl == 0;
+  SolveScratch& sg = es.s[member ? g : 0];
+  if (leader) {
+    if (live) {
+      double a[2 * kSampleH], b[2 * kSampleH];
+      for (int k = 0; k < 2 * kSampleH; ++k) { a[k] = x1[8 * t + k]; b[k] = x2[8 * t + k]; }
+      four_point_qr(a, b, es.u.A[g], sg.W, sg.V);
+    } else {
+      for (int i = 0; i < 81; ++i) { sg.W[i] = 0.0; sg.V[i] = 0.0; }
+    }
   }
   __syncwarp();
-  jacobi_svd9_sweeps_warp(ws.W, ws.V, lane);
-  if (lane == 0) {
-    for (int q = 0; q < 9; ++q) { ws.F[q] = ws.V[q + 9 * 8]; H[9 * t + q] = ws.F[q]; }
-    err[t] = homography_error(ws.F, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
+  jacobi_svd9_sweeps_groups(es, lane);
+  if (leader && live) {
+    for (int q = 0; q < 9; ++q) { sg.F[q] = sg.V[q + 9 * 8]; H[9 * t + q] = sg.F[q]; }
+    err[t] = homography_error(sg.F, probe[4 * t], probe[4 * t + 1], probe[4 * t + 2], probe[4 * t + 3]);
   }
 }
 

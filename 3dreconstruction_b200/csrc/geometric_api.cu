@@ -169,7 +169,8 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   int n_cap = 32;
   while (n_cap < n_max) n_cap <<= 1;
   const int it_stride = iterations + 8;
-  const int max_wave_warps = 2 * ((iterations + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;  // ranges evaluated in one launch
+  // ranges evaluated in one launch, in warps (a warp takes kEvalGroup iterations)
+  const int max_wave_warps = 2 * ((iterations / kEvalGroup + 1 + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
   if (!active.empty()) {
     GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
@@ -316,10 +317,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       for (int q = 0; q < kGeoSlots; ++q) {
         HostSlot& H = slots[q];
         if (H.state == kNeedEval) {
-          const int n_it = H.hi - H.lo;
-          if (EL.first_warp[EL.n] + n_it > max_wave_warps && EL.n > 0) continue;  // next wave
+          const int n_w = (H.hi - H.lo + kEvalGroup - 1) / kEvalGroup;
+          if (EL.first_warp[EL.n] + n_w > max_wave_warps && EL.n > 0) continue;  // next wave
           EL.slot[EL.n] = q;
-          EL.first_warp[EL.n + 1] = EL.first_warp[EL.n] + n_it;
+          EL.first_warp[EL.n + 1] = EL.first_warp[EL.n] + n_w;
           ++EL.n;
           DL.slot[DL.n++] = q;
         } else if (H.state == kNeedExact) {
@@ -477,7 +478,7 @@ extern "C" int mvgcuda_geo_selftest_h(mvgcuda_ctx* ctx, int n, const double* x1,
   if (e == cudaSuccess) e = cudaMemcpy(d_x2.p, x2, (size_t)n * 8 * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_p.p, probe, (size_t)n * 4 * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    geo_selftest_h_kernel<<<n, 32>>>(n, d_x1.p, d_x2.p, d_p.p, d_H.p, d_e.p);
+    geo_selftest_h_kernel<<<(n + kEvalGroup - 1) / kEvalGroup, 32>>>(n, d_x1.p, d_x2.p, d_p.p, d_H.p, d_e.p);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(H, d_H.p, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost);
