@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <map>
 #include <new>
+#include <algorithm>
+#include <deque>
 #include <vector>
 
 #include "../../include/mvgcuda.h"
@@ -169,8 +171,8 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   int n_cap = 32;
   while (n_cap < n_max) n_cap <<= 1;
   const int it_stride = iterations + 8;
-  // ranges evaluated in one launch, in warps (a warp takes kEvalGroup iterations)
-  const int max_wave_warps = 2 * ((iterations / kEvalGroup + 1 + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
+  // ranges evaluated in one launch, in warps (a warp takes kEvalGroup iterations): the first phases of four pairs
+  const int max_wave_warps = 4 * ((iterations / kEvalGroup + 1 + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
   if (!active.empty()) {
     GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
@@ -186,7 +188,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, G.h_state.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_round.reserve(kGeoSlots));
   }
-  long long exact_requests = 0, waves = 0;
+  long long exact_requests = 0, waves = 0, respeculated = 0;
 
   // ---- the process-wide rand() stream: srand(seed) here, consumed pair after pair (the reference never seeds: seed 1)
   GlibcRand gen;
@@ -286,28 +288,47 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     // Every wave: range evaluations of the slots that need one (one warp per iteration), re-evaluations with roots from
     // THIS machine's C library for the slots that asked, the accounting warp of every slot that was served, one
     // synchronisation.
-    enum { kFree = 0, kNeedEval = 1, kNeedExact = 2 };
-    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; };
+    //
+    // Speculative starts: a pair that finds no meaningful model runs exactly `iterations` iterations, and in a large
+    // exhaustive collection most pairs are of that kind.  After two such pairs in a row up to kSpecDepth FURTHER pairs are
+    // started at the offsets that assumption gives (each is an upper bound, so the stream window covers them); when a
+    // pair's count becomes final the next one is either confirmed (its offset was right: nothing to do) or every pair
+    // started after it is restarted from the corrected offset.  A speculative pair that finishes early is held in its slot
+    // until its offset is confirmed.  Pairs with geometry end the streak and the chain goes back to one start at a time.
+    enum { kFree = 0, kNeedEval = 1, kNeedExact = 2, kHeldDone = 3 };
+    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; };
     HostSlot slots[kGeoSlots];
     int next_admit = 0, done_pairs = 0;
-    int chain_tail = -1;            // slot of the youngest pair in flight while its iteration count is still open
-    long long chain_offset = offset;
+    std::deque<int> chain;          // slots of the pairs in flight whose iteration count is still open, oldest first; only
+                                    // the front one has a definite offset, the others were started speculatively
+    long long chain_offset = offset;  // offset of the next pair when the chain is empty
+    int noise_streak = 0;           // pairs in a row that consumed the whole budget
+    constexpr int kSpecDepth = 3;
+    auto start_pair = [&](int sl, int pair, long long off) -> int {
+      AcState S0;
+      ac_init(S0, G.h_pairs.p[pair].n, iterations, sample);
+      RoundInfo R0;
+      R0.pair = pair; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = off;
+      G.h_state.p[sl] = S0;
+      G.h_round.p[sl] = R0;
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, st));
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, st));
+      HostSlot& H = slots[sl];
+      H.state = kNeedEval; H.pair = pair; H.lo = R0.lo; H.hi = R0.hi; H.offset = off; H.iters_final = -1;
+      return MVGCUDA_OK;
+    };
     while (done_pairs < nb) {
       // admissions
-      while (next_admit < nb && chain_tail < 0) {
+      while (next_admit < nb) {
+        const int depth = noise_streak >= 2 ? kSpecDepth : 0;
+        if ((int)chain.size() > depth) break;
         int sl = -1;
         for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kFree) { sl = q; break; }
         if (sl < 0) break;
-        AcState S0;
-        ac_init(S0, G.h_pairs.p[next_admit].n, iterations, sample);
-        RoundInfo R0;
-        R0.pair = next_admit; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = chain_offset;
-        G.h_state.p[sl] = S0;
-        G.h_round.p[sl] = R0;
-        GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, st));
-        GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, st));
-        slots[sl].state = kNeedEval; slots[sl].pair = next_admit; slots[sl].lo = R0.lo; slots[sl].hi = R0.hi;
-        chain_tail = sl;
+        const long long off = chain.empty() ? chain_offset : slots[chain.back()].offset + (long long)sample * iterations;
+        rc = start_pair(sl, next_admit, off);
+        if (rc) return rc;
+        chain.push_back(sl);
         ++next_admit;
       }
       // this wave's work lists
@@ -351,19 +372,42 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         const int q = DL.slot[k];
         HostSlot& H = slots[q];
         const DecideOut& D = G.h_decide.p[q];
-        if (q == chain_tail && D.iters_final >= 0) {
-          chain_offset += (long long)sample * D.iters_final;
-          chain_tail = -1;
-        }
+        if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
         if (D.status == 1) {
           H.state = kNeedExact; H.it = D.it;
           for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
         } else if (D.status == 2) {
-          H.state = kFree; H.pair = -1;
-          ++done_pairs;
+          const bool speculative = std::find(chain.begin(), chain.end(), q) != chain.end() && chain.front() != q;
+          if (speculative) {
+            H.state = kHeldDone;     // its offset is not confirmed yet
+          } else {
+            H.state = kFree;
+            ++done_pairs;
+          }
         } else {
           H.state = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
         }
+      }
+      // the chain: a front pair whose count is final leaves it and confirms or refutes the offset of the next one
+      while (!chain.empty() && slots[chain.front()].iters_final >= 0) {
+        const HostSlot& F = slots[chain.front()];
+        const long long next_off = F.offset + (long long)sample * F.iters_final;
+        noise_streak = F.iters_final == iterations ? noise_streak + 1 : 0;
+        chain.pop_front();
+        if (chain.empty()) { chain_offset = next_off; break; }
+        if (slots[chain.front()].offset == next_off) {
+          HostSlot& N = slots[chain.front()];
+          if (N.state == kHeldDone) { N.state = kFree; ++done_pairs; }   // (its count is final too: it leaves on the next turn)
+          continue;
+        }
+        long long off = next_off;   // refuted: everything started after it starts again
+        for (size_t c = 0; c < chain.size(); ++c) {
+          rc = start_pair(chain[c], slots[chain[c]].pair, off);
+          if (rc) return rc;
+          off += (long long)sample * iterations;
+        }
+        ++respeculated;
+        break;
       }
     }
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_count.p, G.d_out_count.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -407,6 +451,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   GEO_CHECK(ctx, G.r_matches.reserve((size_t)std::max<long long>(total, 1) * 2));
   for (size_t a = 0; a < active.size(); ++a)
     if (!kept[a].empty()) memcpy(G.r_matches.p + 2 * G.r_offsets.p[active[a]], kept[a].data(), kept[a].size() * sizeof(int32_t));
+  if (const char* v = getenv("MVGCUDA_GEO_STATS"))
+    if (*v == '1')
+      fprintf(stderr, "mvgcuda_geometric_filter('%c'): %zu active pairs, %lld waves, %d launches, %lld models re-evaluated with host roots, "
+                      "%lld speculative starts refuted, %lld rand() values\n", model, active.size(), waves, launches, exact_requests, respeculated, offset);
   if (out) {
     out->n_pairs = n_pairs;
     out->counts = G.r_counts.p;
