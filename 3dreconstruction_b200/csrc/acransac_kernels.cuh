@@ -64,6 +64,7 @@ constexpr int kGeoSlots = 16;
 
 struct EvalList {    // one wave of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1])
   int n;
+  int group;         // iterations a warp takes: kEvalGroup when the wave is wide (throughput), 1 when it is narrow (latency)
   int slot[kGeoSlots];
   int first_warp[kGeoSlots + 1];
 };
@@ -378,7 +379,7 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   if (gwarp >= L.first_warp[L.n]) return;
   const SlotView V = slot_view(B, L.slot[k]);
   const RoundInfo R = *V.round;
-  const int it0 = R.lo + kEvalGroup * (gwarp - L.first_warp[k]);
+  const int it0 = R.lo + L.group * (gwarp - L.first_warp[k]);
   if (it0 >= R.hi) return;
   const GeoPairDev P = B.pairs[R.pair];
   const bool identity = V.state->index_it < 0;
@@ -388,7 +389,7 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   const int g = lane / kGroupLanes, gl = lane - g * kGroupLanes;
   const bool member = g < kEvalGroup;
   const int it = it0 + g;
-  const bool live = member && it < R.hi;          // the group has an iteration to solve
+  const bool live = g < L.group && it < R.hi;     // the group has an iteration to solve
   const bool leader = member && gl == 0;
   SolveScratch& sg = es.s[member ? g : 0];
   const uint32_t* rs = B.stream + (R.offset + static_cast<long long>(B.sample) * it - B.stream_base);
@@ -455,7 +456,7 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
     }
   }
   __syncwarp();
-  for (int q = 0; q < kEvalGroup && it0 + q < R.hi; ++q) {
+  for (int q = 0; q < L.group && it0 + q < R.hi; ++q) {
     const IterRes r = evaluate_models_warp(B, P, es.s[q].F, es.u.list.le, es.u.list.li, es.s[q].n_models, ge, gi, lane);
     if (lane == 0) { V.res[it0 + q] = r; V.exact[it0 + q] = B.model; }  // a homography model needs no second look
     __syncwarp();

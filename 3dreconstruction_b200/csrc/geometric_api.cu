@@ -26,6 +26,7 @@ namespace {
 constexpr int kGeoBatchPairs = 1024;        // active pairs per launch
 constexpr long long kGeoBatchMatches = 4ll << 20;
 constexpr int kGeoMaxMatchesPerPair = 16384;
+constexpr int kNarrowWaveIterations = 148 * 8;  // up to eight warps per SM: nothing to gain from packing three iterations into one
 
 struct GeoState {
   DevBuf<GeoPairDev> d_pairs;
@@ -333,12 +334,18 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       }
       // this wave's work lists
       EvalList EL; EL.n = 0; EL.first_warp[0] = 0;
+      {  // a narrow wave is bound by the latency of one warp (the SVD chain, then its evaluations one after the other): one
+         // iteration per warp then; a wide one by the fp64 pipe: three
+        long long pending = 0;
+        for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kNeedEval) pending += slots[q].hi - slots[q].lo;
+        EL.group = pending <= kNarrowWaveIterations ? 1 : kEvalGroup;
+      }
       ExactList XL; XL.n = 0;
       DecideList DL; DL.n = 0;
       for (int q = 0; q < kGeoSlots; ++q) {
         HostSlot& H = slots[q];
         if (H.state == kNeedEval) {
-          const int n_w = (H.hi - H.lo + kEvalGroup - 1) / kEvalGroup;
+          const int n_w = (H.hi - H.lo + EL.group - 1) / EL.group;
           if (EL.first_warp[EL.n] + n_w > max_wave_warps && EL.n > 0) continue;  // next wave
           EL.slot[EL.n] = q;
           EL.first_warp[EL.n + 1] = EL.first_warp[EL.n] + n_w;
