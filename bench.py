@@ -222,6 +222,55 @@ def geometric_filter_leg(ctx, pkg, pm, pairs, feats, n_pairs=192, cpu_pairs=12):
         cdt = time.time() - t0
         out["cpu_reference"] = {"value": done / cdt, "unit": "pairs/s", "cores": 1, "kind": "reference",
                                 "sample": f"{done} of those pairs through the reference's own ACRANSAC + 7-point kernel (oracle/_ref/libmvgref_geom.so), one host thread"}
+    # the same putatives through the homography functor (compute_matches -g h)
+    ctx.geometric_filter(put, sizes, model="h")
+    t0 = time.time()
+    res_h = ctx.geometric_filter(put, sizes, model="h")
+    out["homography"] = {"gpu_pairs_per_s": int((put.counts > 4).sum()) / (time.time() - t0), "gpu_ms_on_stream": res_h.timing["gpu_ms"],
+                         "rand_values_consumed": int(res_h.timing["rand_consumed"]), "pairs_kept": int((res_h.counts > 0).sum())}
+    # pairs WITH geometry (the other regime: ~9 accepted models per pair, the chain of pair starts is the limit): a planted
+    # 3-D scene seen by 16 cameras, 200 putatives per pair of which 60 % are true correspondences
+    rng = np.random.default_rng(7)
+    n_pts, n_cam = 1200, 16
+    X = np.stack([rng.uniform(-2.2, 2.2, n_pts), rng.uniform(-1.6, 1.6, n_pts), rng.uniform(6, 14, n_pts)], 1)
+    pf = []
+    for k in range(n_cam):
+        th = 0.03 * (k - n_cam / 2)
+        R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+        Xc = X @ R.T + np.array([0.15 * (k - n_cam / 2), 0.02 * k, 0.05 * k])
+        xy = np.stack([3600 * Xc[:, 0] / Xc[:, 2] + 2000, 3600 * Xc[:, 1] / Xc[:, 2] + 1500], 1) + rng.normal(0, 0.6, (n_pts, 2))
+        pf.append(np.concatenate([np.clip(xy, 0, [3999, 2999]), np.stack([rng.uniform(0, 4000, 400), rng.uniform(0, 3000, 400)], 1)]).astype(np.float32))
+    d = {}
+    for i in range(n_cam):
+        for j in range(i + 1, n_cam):
+            idx = rng.permutation(n_pts)[:120]
+            m = np.stack([np.concatenate([idx, rng.integers(0, n_pts + 400, 80)]), np.concatenate([idx, rng.integers(0, n_pts + 400, 80)])], 1)
+            d[(i, j)] = m[np.argsort(m[:, 1], kind="stable")]
+    planted = pkg.PairMatches.from_dict(d)
+    ctx2 = pkg.Context(ctx.device if hasattr(ctx, "device") else 0)
+    ctx2.upload_images([np.zeros((len(f), 128), np.uint8) for f in pf])
+    ctx2.set_features(pf)
+    ctx2.geometric_filter(planted, [(4000, 3000)] * n_cam)
+    t0 = time.time()
+    res_p = ctx2.geometric_filter(planted, [(4000, 3000)] * n_cam)
+    dtp = time.time() - t0
+    out["planted_geometry"] = {"pairs": len(d), "matches_per_pair": 200, "gpu_pairs_per_s": len(d) / dtp, "gpu_ms_on_stream": res_p.timing["gpu_ms"],
+                               "pairs_kept": int((res_p.counts > 0).sum()), "matches_kept": int(res_p.counts.sum()),
+                               "models_reevaluated_with_host_roots": int(res_p.timing["knn_kernel_launches"])}
+    if os.path.exists(lib_path):
+        t0, done = time.time(), 0
+        for p in range(min(cpu_pairs * 2, len(planted.pairs))):
+            i, j = planted.pairs[p]
+            m = planted.pair(p)
+            xI = np.ascontiguousarray(pf[i][m[:, 0]], np.float32)
+            xJ = np.ascontiguousarray(pf[j][m[:, 1]], np.float32)
+            inl = (C.c_int * (len(m) + 1))()
+            o = (C.c_double * 3)()
+            ref.ref_acransac_f(xI.ctypes.data_as(fp), xJ.ctypes.data_as(fp), len(m), 4000, 3000, 4000, 3000, 4.0, 4096, 1, inl, o)
+            done += 1
+        out["planted_geometry"]["cpu_reference"] = {"value": done / (time.time() - t0), "unit": "pairs/s", "cores": 1, "kind": "reference",
+                                                    "sample": f"{done} of those pairs, one host thread"}
+    del ctx2
     return out
 
 
