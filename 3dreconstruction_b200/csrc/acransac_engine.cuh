@@ -57,16 +57,18 @@ MVG_GEO_HD void ac_init(AcState& S, int n_data, int max_iterations, int sample_s
 // Upper end of the range to evaluate next with the current vec_index.
 MVG_GEO_HD int ac_range_end(const AcState& S) { return S.extend_to > 0 ? S.extend_to : S.iter_num; }
 
-// Account for the evaluated range [S.iter, ac_range_end(S)).  Returns 1 when vec_index changed (evaluate again from S.iter),
-// 0 otherwise; S.done is set when the loop has ended.
+// Account for the evaluated range [S.iter, hi) -- hi = ac_range_end(S), or less (hi_eval) when only the head of the first
+// phase has been evaluated so far.  Returns 1 when there is more to evaluate from S.iter (vec_index changed, or the rest of
+// a partly evaluated range), 0 otherwise; S.done is set when the loop has ended.
 template <typename Range>
-MVG_GEO_HD int ac_account(AcState& S, const Range& R) {
-  const int lo = S.iter, hi = ac_range_end(S);
+MVG_GEO_HD int ac_account(AcState& S, const Range& R, int hi_eval = -1) {
+  const int lo = S.iter, hi_full = ac_range_end(S);
+  const int hi = (hi_eval >= 0 && hi_eval < hi_full) ? hi_eval : hi_full;
   if (S.extend_to > 0) {
     // The first phase ended with no model at all (vec_inliers empty): every further iteration that finds nothing does
     // iter_num++, nIterReserve-- (:223-226); the first one with ANY model makes its inliers the sampling set and spends what
-    // is left of the reserve (:228-234), so the loop always ends at the same total.
-    const int t = lo < hi ? R.first_below(lo, hi, ac_inf()) : -1;
+    // is left of the reserve (:228-234), so the loop always ends at the same total.  (Never evaluated in parts.)
+    const int t = lo < hi_full ? R.first_below(lo, hi_full, ac_inf()) : -1;
     const int total = S.extend_to;
     S.extend_to = 0;
     S.reserve = 0;
@@ -92,8 +94,15 @@ MVG_GEO_HD int ac_account(AcState& S, const Range& R) {
     if (S.iter >= S.iter_num) S.done = 1;
     return S.done ? 0 : 1;
   }
-  // no trigger: only a non-negative minNFA can still have improved (strictly, first occurrence)
-  const int a = R.argmin_first(lo, hi);
+  if (hi < hi_full) {
+    // the head of the first phase holds no trigger: go on with the same (identity) sampling set; the non-negative minimum is
+    // folded once, when the whole phase has been evaluated (below: from iteration 0)
+    S.iter = hi;
+    return 1;
+  }
+  // no trigger: only a non-negative minNFA can still have improved (strictly, first occurrence).  In the first phase the
+  // range starts at iteration 0 whatever parts it was evaluated in.
+  const int a = R.argmin_first(S.reserve ? 0 : lo, hi);
   if (R.nfa(a) < S.min_nfa) { S.min_nfa = R.nfa(a); S.best_it = a; S.best_model = R.model(a); S.n_inl = R.n_inl(a); }
   S.iter = hi;
   if (S.reserve) {  // iter + 1 == iter_num && nIterReserve (:221)

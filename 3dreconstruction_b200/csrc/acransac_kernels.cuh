@@ -64,7 +64,8 @@ constexpr int kGeoSlots = 16;
 
 struct EvalList {    // one wave of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1])
   int n;
-  int group;         // iterations a warp takes: kEvalGroup when the wave is wide (throughput), 1 when it is narrow (latency)
+  int group;         // iterations a warp takes: kEvalGroup when the range is wide (throughput), 1 when it is narrow (latency)
+  int scratch_base;  // first warp-scratch list of this launch (launches of different slots run side by side)
   int slot[kGeoSlots];
   int first_warp[kGeoSlots + 1];
 };
@@ -384,8 +385,8 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   const GeoPairDev P = B.pairs[R.pair];
   const bool identity = V.state->index_it < 0;
   EvalScratch& es = scratch[warp];
-  double* ge = B.g_e + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
-  int* gi = B.g_i + static_cast<size_t>(kGeoSlots + gwarp) * B.n_cap;
+  double* ge = B.g_e + static_cast<size_t>(kGeoSlots + L.scratch_base + gwarp) * B.n_cap;
+  int* gi = B.g_i + static_cast<size_t>(kGeoSlots + L.scratch_base + gwarp) * B.n_cap;
   const int g = lane / kGroupLanes, gl = lane - g * kGroupLanes;
   const bool member = g < kEvalGroup;
   const int it = it0 + g;
@@ -542,7 +543,11 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
   const RoundInfo R = *V.round;
   const GeoPairDev P = B.pairs[R.pair];
   AcState S = *V.state;
-  const int lo = S.iter, hi = ac_range_end(S);
+  // the evaluated range: the whole pending one, or only the head of the first phase (the host starts a pair with a short
+  // first range when pairs with geometry are about: their trigger sits in the first few dozen iterations)
+  const int lo = S.iter, hi_full = ac_range_end(S);
+  const int hi = R.hi < hi_full ? R.hi : hi_full;
+  const bool head_only = hi < hi_full;
   if (!S.done && lo < hi) {
     const bool ext = S.extend_to > 0;
     const double thr = ext ? ac_inf() : (S.min_nfa < 0.0 ? S.min_nfa : 0.0);
@@ -552,18 +557,19 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
     const int t = first_candidate(V, lo, hi, thr, guard, lane);
     if (t >= 0) {
       if (!V.exact[t]) need = t;
-    } else if (!ext && S.reserve > 0) {
+    } else if (!ext && S.reserve > 0 && !head_only) {
       // no iteration of the whole first phase can be a trigger (none within the guard band of 0), so the loop will run
       // iter_num + reserve iterations whichever model the fold below settles on: the next pair may start already
       no_trigger_in_phase_one = true;
-      // end of the first phase without a trigger: the best model so far becomes the sampling set -- the minimum must be exact
+      // end of the first phase without a trigger: the best model so far becomes the sampling set -- the minimum must be
+      // exact (over the whole phase, from iteration 0, whatever parts it was evaluated in)
       const WarpRange WR{V.res, lane};
-      const int a = WR.argmin_first(lo, hi);
+      const int a = WR.argmin_first(0, hi);
       const double m = V.res[a].nfa;
       if (m < ac_inf()) {
         const double g2 = kGuardAbs + kGuardRel * fabs(m);
         int f = 0x7fffffff;
-        for (int i = lo + lane; i < hi; i += 32)
+        for (int i = lane; i < hi; i += 32)
           if (!V.exact[i] && V.res[i].nfa <= m + g2) { f = i; break; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
@@ -583,7 +589,7 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
   }
   const WarpRange WR{V.res, lane};
   const int old_it = S.index_it, old_model = S.index_model;
-  ac_account(S, WR);
+  ac_account(S, WR, head_only ? hi : -1);
   if (!S.done && (S.index_it != old_it || S.index_model != old_model)) {
     double* e;
     int* idx;

@@ -26,7 +26,7 @@ namespace {
 constexpr int kGeoBatchPairs = 1024;        // active pairs per launch
 constexpr long long kGeoBatchMatches = 4ll << 20;
 constexpr int kGeoMaxMatchesPerPair = 16384;
-constexpr int kNarrowWaveIterations = 148 * 8;  // up to eight warps per SM: nothing to gain from packing three iterations into one
+constexpr int kNarrowRangeIterations = 148 * 4;  // a range of up to four warps per SM: latency-bound, nothing to gain from packing three iterations into one warp
 
 struct GeoState {
   DevBuf<GeoPairDev> d_pairs;
@@ -58,7 +58,9 @@ struct GeoState {
   int logc_k_sample = 0;  // the MINIMUM_SAMPLES the table was built for
   std::vector<float> logc_pool;
   std::map<int, int> logc_off;  // n -> offset in the pool
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_prep = nullptr;
+  cudaStream_t slot_stream[kGeoSlots] = {};   // every pair in flight advances on its own stream
+  cudaEvent_t slot_ev[kGeoSlots] = {};
 };
 
 void geo_free(void* p) {
@@ -73,6 +75,11 @@ void geo_free(void* p) {
   G->h_offsets.release(); G->r_counts.release(); G->r_offsets.release(); G->r_matches.release();
   if (G->ev0) cudaEventDestroy(G->ev0);
   if (G->ev1) cudaEventDestroy(G->ev1);
+  if (G->ev_prep) cudaEventDestroy(G->ev_prep);
+  for (int q = 0; q < kGeoSlots; ++q) {
+    if (G->slot_ev[q]) cudaEventDestroy(G->slot_ev[q]);
+    if (G->slot_stream[q]) cudaStreamDestroy(G->slot_stream[q]);
+  }
   delete G;
 }
 
@@ -115,6 +122,13 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   }
   GeoState& G = *static_cast<GeoState*>(*V.geo);
   if (!G.ev0) { GEO_CHECK(ctx, cudaEventCreate(&G.ev0)); GEO_CHECK(ctx, cudaEventCreate(&G.ev1)); }
+  if (!G.ev_prep) {
+    GEO_CHECK(ctx, cudaEventCreateWithFlags(&G.ev_prep, cudaEventDisableTiming));
+    for (int q = 0; q < kGeoSlots; ++q) {
+      GEO_CHECK(ctx, cudaStreamCreateWithFlags(&G.slot_stream[q], cudaStreamNonBlocking));
+      GEO_CHECK(ctx, cudaEventCreateWithFlags(&G.slot_ev[q], cudaEventDisableTiming));
+    }
+  }
   cudaStream_t st = V.stream;
   int rc = ctx_wait_uploads(ctx);
   if (rc) return rc;
@@ -172,8 +186,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   int n_cap = 32;
   while (n_cap < n_max) n_cap <<= 1;
   const int it_stride = iterations + 8;
-  // ranges evaluated in one launch, in warps (a warp takes kEvalGroup iterations): the first phases of four pairs
-  const int max_wave_warps = 4 * ((iterations / kEvalGroup + 1 + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
+  // warps of one range evaluation (one iteration per warp in a narrow range, kEvalGroup in a wide one); every slot has its
+  // own region of warp-scratch lists, so that the launches of different slots can run side by side
+  const int slot_warps = ((std::max(std::min(iterations, kNarrowRangeIterations), iterations / kEvalGroup + 1) + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
+  const int max_wave_warps = kGeoSlots * slot_warps;
   if (!active.empty()) {
     GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
@@ -282,13 +298,13 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p; B.out_iters = G.d_out_iters.p;
     geo_prep_kernel<<<nb, 256, 0, st>>>(B);
     GEO_CHECK(ctx, cudaGetLastError());
+    GEO_CHECK(ctx, cudaEventRecord(G.ev_prep, st));
     ++launches;
 
-    // The wavefront.  The chain orders only the STARTS of the pairs: pair p + 1 is admitted (into a free slot) as soon as
-    // pair p's iteration count is final -- its rand() offset follows -- and from then on the two advance side by side.
-    // Every wave: range evaluations of the slots that need one (one warp per iteration), re-evaluations with roots from
-    // THIS machine's C library for the slots that asked, the accounting warp of every slot that was served, one
-    // synchronisation.
+    // The pipeline.  The chain orders only the STARTS of the pairs: pair p + 1 is admitted (into a free slot) as soon as
+    // pair p's iteration count is final -- its rand() offset follows -- and from then on each advances on its own stream:
+    // evaluation of its pending range (or the re-evaluation of one iteration with roots from THIS machine's C library),
+    // its accounting warp, the copy of the verdict, an event the host polls.  No pair waits for another one's kernels.
     //
     // Speculative starts: a pair that finds no meaningful model runs exactly `iterations` iterations, and in a large
     // exhaustive collection most pairs are of that kind.  After two such pairs in a row up to kSpecDepth FURTHER pairs are
@@ -297,7 +313,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     // started after it is restarted from the corrected offset.  A speculative pair that finishes early is held in its slot
     // until its offset is confirmed.  Pairs with geometry end the streak and the chain goes back to one start at a time.
     enum { kFree = 0, kNeedEval = 1, kNeedExact = 2, kHeldDone = 3 };
-    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; };
+    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; bool in_flight = false, discard = false; };
     HostSlot slots[kGeoSlots];
     int next_admit = 0, done_pairs = 0;
     std::deque<int> chain;          // slots of the pairs in flight whose iteration count is still open, oldest first; only
@@ -305,16 +321,23 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     long long chain_offset = offset;  // offset of the next pair when the chain is empty
     int noise_streak = 0;           // pairs in a row that consumed the whole budget
     constexpr int kSpecDepth = 3;
+    constexpr int kFirstRange = 192;  // iterations of a pair's first range while pairs with geometry are about
     auto start_pair = [&](int sl, int pair, long long off) -> int {
       AcState S0;
       ac_init(S0, G.h_pairs.p[pair].n, iterations, sample);
       RoundInfo R0;
       R0.pair = pair; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = off;
+      // pairs with geometry about: only the head of the first phase at first -- their trigger is almost always in it, and
+      // everything evaluated after a trigger is thrown away (a no-model pair pays one more round for the rest)
+      if (noise_streak < 2 && R0.hi > kFirstRange) R0.hi = kFirstRange;
       G.h_state.p[sl] = S0;
       G.h_round.p[sl] = R0;
-      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, st));
-      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, st));
+      GEO_CHECK(ctx, cudaStreamWaitEvent(G.slot_stream[sl], G.ev_prep, 0));  // the batch's points are normalised
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, G.slot_stream[sl]));
+      GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, G.slot_stream[sl]));
       HostSlot& H = slots[sl];
+      // (a restart while the slot's previous launches are still running: they come first in its stream; their verdict is dropped)
+      if (H.in_flight) H.discard = true;
       H.state = kNeedEval; H.pair = pair; H.lo = R0.lo; H.hi = R0.hi; H.offset = off; H.iters_final = -1;
       return MVGCUDA_OK;
     };
@@ -332,68 +355,78 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         chain.push_back(sl);
         ++next_admit;
       }
-      // this wave's work lists
-      EvalList EL; EL.n = 0; EL.first_warp[0] = 0;
-      {  // a narrow wave is bound by the latency of one warp (the SVD chain, then its evaluations one after the other): one
-         // iteration per warp then; a wide one by the fp64 pipe: three
-        long long pending = 0;
-        for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kNeedEval) pending += slots[q].hi - slots[q].lo;
-        EL.group = pending <= kNarrowWaveIterations ? 1 : kEvalGroup;
-      }
-      ExactList XL; XL.n = 0;
-      DecideList DL; DL.n = 0;
+      // launches: every slot with something to do and nothing in flight gets, on ITS stream, the evaluation of its
+      // pending range (or the re-evaluation of one iteration with roots from this machine's C library), its accounting
+      // warp and the copy of the verdict; the slots advance independently of each other
       for (int q = 0; q < kGeoSlots; ++q) {
         HostSlot& H = slots[q];
+        if (H.in_flight || (H.state != kNeedEval && H.state != kNeedExact)) continue;
+        cudaStream_t sq = G.slot_stream[q];
         if (H.state == kNeedEval) {
+          EvalList EL;
+          EL.n = 1; EL.slot[0] = q; EL.first_warp[0] = 0;
+          // a narrow range is bound by the latency of one warp (the SVD chain, then its evaluations one after the other):
+          // one iteration per warp; a wide one by the fp64 pipe: three
+          EL.group = (H.hi - H.lo) <= kNarrowRangeIterations ? 1 : kEvalGroup;
+          EL.scratch_base = q * slot_warps;
           const int n_w = (H.hi - H.lo + EL.group - 1) / EL.group;
-          if (EL.first_warp[EL.n] + n_w > max_wave_warps && EL.n > 0) continue;  // next wave
-          EL.slot[EL.n] = q;
-          EL.first_warp[EL.n + 1] = EL.first_warp[EL.n] + n_w;
-          ++EL.n;
-          DL.slot[DL.n++] = q;
-        } else if (H.state == kNeedExact) {
-          XL.slot[XL.n] = q; XL.it[XL.n] = H.it;
-          XL.nr[XL.n] = solve_cubic(H.P, XL.roots[XL.n]);  // host libm: acos / cos / pow as the reference's process would call them
-          ++XL.n;
-          DL.slot[DL.n++] = q;
-          ++exact_requests;
-        }
-      }
-      if (EL.n > 0 && EL.first_warp[EL.n] > 0) {
-        geo_eval_kernel<<<(EL.first_warp[EL.n] + kEvalWarps - 1) / kEvalWarps, 32 * kEvalWarps, 0, st>>>(B, EL);
-        GEO_CHECK(ctx, cudaGetLastError());
-        ++launches;
-      }
-      if (XL.n > 0) {
-        geo_exact_kernel<<<XL.n, 32, 0, st>>>(B, XL);
-        GEO_CHECK(ctx, cudaGetLastError());
-        ++launches;
-      }
-      geo_decide_kernel<<<DL.n, 32, 0, st>>>(B, DL);
-      GEO_CHECK(ctx, cudaGetLastError());
-      ++launches;
-      ++waves;
-      GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p, G.d_decide.p, kGeoSlots * sizeof(DecideOut), cudaMemcpyDeviceToHost, st));
-      GEO_CHECK(ctx, cudaStreamSynchronize(st));
-      for (int k = 0; k < DL.n; ++k) {
-        const int q = DL.slot[k];
-        HostSlot& H = slots[q];
-        const DecideOut& D = G.h_decide.p[q];
-        if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
-        if (D.status == 1) {
-          H.state = kNeedExact; H.it = D.it;
-          for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
-        } else if (D.status == 2) {
-          const bool speculative = std::find(chain.begin(), chain.end(), q) != chain.end() && chain.front() != q;
-          if (speculative) {
-            H.state = kHeldDone;     // its offset is not confirmed yet
-          } else {
-            H.state = kFree;
-            ++done_pairs;
+          EL.first_warp[1] = n_w;
+          if (n_w > 0) {
+            geo_eval_kernel<<<(n_w + kEvalWarps - 1) / kEvalWarps, 32 * kEvalWarps, 0, sq>>>(B, EL);
+            GEO_CHECK(ctx, cudaGetLastError());
+            ++launches;
           }
         } else {
-          H.state = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
+          ExactList XL;
+          XL.n = 1; XL.slot[0] = q; XL.it[0] = H.it;
+          XL.nr[0] = solve_cubic(H.P, XL.roots[0]);  // host libm: acos / cos / pow as the reference's process would call them
+          geo_exact_kernel<<<1, 32, 0, sq>>>(B, XL);
+          GEO_CHECK(ctx, cudaGetLastError());
+          ++launches;
+          ++exact_requests;
         }
+        DecideList DL;
+        DL.n = 1; DL.slot[0] = q;
+        geo_decide_kernel<<<1, 32, 0, sq>>>(B, DL);
+        GEO_CHECK(ctx, cudaGetLastError());
+        ++launches;
+        ++waves;
+        GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p + q, G.d_decide.p + q, sizeof(DecideOut), cudaMemcpyDeviceToHost, sq));
+        GEO_CHECK(ctx, cudaEventRecord(G.slot_ev[q], sq));
+        H.in_flight = true;
+      }
+      // wait until at least one slot has its verdict, then take every verdict that is there
+      int completed = 0;
+      while (!completed) {
+        bool any_in_flight = false;
+        for (int q = 0; q < kGeoSlots; ++q) {
+          HostSlot& H = slots[q];
+          if (!H.in_flight) continue;
+          any_in_flight = true;
+          const cudaError_t qe = cudaEventQuery(G.slot_ev[q]);
+          if (qe == cudaErrorNotReady) continue;
+          GEO_CHECK(ctx, qe);
+          H.in_flight = false;
+          ++completed;
+          if (H.discard) { H.discard = false; continue; }   // the verdict of a refuted start
+          const DecideOut& D = G.h_decide.p[q];
+          if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
+          if (D.status == 1) {
+            H.state = kNeedExact; H.it = D.it;
+            for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
+          } else if (D.status == 2) {
+            const bool speculative = std::find(chain.begin(), chain.end(), q) != chain.end() && chain.front() != q;
+            if (speculative) {
+              H.state = kHeldDone;     // its offset is not confirmed yet
+            } else {
+              H.state = kFree;
+              ++done_pairs;
+            }
+          } else {
+            H.state = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
+          }
+        }
+        if (!any_in_flight) return fail(ctx, "geometric_filter: internal error (no pair in flight)");
       }
       // the chain: a front pair whose count is final leaves it and confirms or refutes the offset of the next one
       while (!chain.empty() && slots[chain.front()].iters_final >= 0) {

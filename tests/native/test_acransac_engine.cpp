@@ -65,7 +65,7 @@ static int candidates(const PairGeo& P, const double* F, std::vector<Cand>& list
 struct Result { std::vector<int> inliers; double nfa, err_max; long used; };
 
 static Result run_engine(char model, const std::vector<float>& xI, const std::vector<float>& xJ, int n, int wI, int hI, int wJ, int hJ,
-                         double precision, int iterations, unsigned seed, long skip = 0, bool verbose = false) {
+                         double precision, int iterations, unsigned seed, long skip = 0, bool verbose = false, int first_chunk = 0) {
   const int sample = model == 'h' ? kSampleH : kSampleF;
   std::vector<double> x1(2 * n), x2(2 * n);
   const Normalizer N1 = make_normalizer(wI, hI), N2 = make_normalizer(wJ, hJ);
@@ -100,7 +100,9 @@ static Result run_engine(char model, const std::vector<float>& xI, const std::ve
   std::vector<Cand> list;
   double W[81], V[81];
   while (!S.done) {
-    const int hi = ac_range_end(S);
+    // (first_chunk > 0: only the head of the first phase is evaluated before the first accounting, as the product does)
+    const bool head = first_chunk > 0 && S.iter == 0 && S.reserve > 0 && S.extend_to == 0 && first_chunk < ac_range_end(S);
+    const int hi = head ? first_chunk : ac_range_end(S);
     for (int it = S.iter; it < hi; ++it) {
       int s[7];
       if (model == 'h') random_sample<4>(&stream[(size_t)4 * it], S.n_index, s);
@@ -122,7 +124,7 @@ static Result run_engine(char model, const std::vector<float>& xI, const std::ve
       }
     }
     HostRange HR{res};
-    ac_account(S, HR);
+    ac_account(S, HR, head ? hi : -1);
     if (verbose) std::printf("  engine: accounted up to %d of %d, minNFA %.17g (it %d, %d inliers), reserve %d\n", S.iter, S.iter_num, S.min_nfa, S.best_it, S.n_inl, S.reserve);
     if (S.index_it != cur_it || S.index_model != cur_model) {
       cur_it = S.index_it; cur_model = S.index_model;
@@ -208,7 +210,7 @@ int main(int argc, char** argv) {
     std::vector<int> want(n + 1);
     double o[3];
     const int nw = (model == 'h' ? ref_acransac_h : ref_acransac_f)(xI.data(), xJ.data(), n, wI, hI, wJ, hJ, precision, iterations, seed, want.data(), o);
-    const Result got = run_engine(model, xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, seed);
+    const Result got = run_engine(model, xI, xJ, n, wI, hI, wJ, hJ, precision, iterations, seed, 0, false, t % 3 == 0 ? 0 : (t % 3 == 1 ? 192 : 7));
     ++cases;
     meaningful += nw > 0;
     bool ok = nw == (int)got.inliers.size() && std::equal(got.inliers.begin(), got.inliers.end(), want.begin());
