@@ -48,11 +48,11 @@ struct RoundInfo {   // what a warp needs to evaluate the current range of a slo
   long long offset;  // absolute rand() position of iteration 0 of the pair
 };
 
-struct DecideOut {   // what the host reads after geo_decide_kernel, per slot
+struct DecideOut {   // the accounting warp's verdict, per slot: written straight into page-locked HOST memory, `seq` last
   int status;        // 0: evaluate `next`, 1: iteration `it` needs exact roots (P), 2: the pair is finished
   int it;
   int iters_final;   // >= 0 once the number of iterations the pair will run is known (the next pair's rand() offset follows)
-  int pad;
+  int seq;           // the launch's sequence number, stored after a system-wide fence: the host polls it
   double P[4];
   RoundInfo next;
 };
@@ -69,14 +69,14 @@ struct EvalList {    // one wave of range evaluations: slot[k] covers warps [fir
   int slot[kGeoSlots];
   int first_warp[kGeoSlots + 1];
 };
-struct ExactList {   // iterations to re-evaluate with the host's roots
+struct ExactList {   // iterations to re-evaluate with the host's roots (the accounting follows in the same warp)
   int n;
-  int slot[kGeoSlots], it[kGeoSlots], nr[kGeoSlots];
+  int slot[kGeoSlots], it[kGeoSlots], nr[kGeoSlots], seq[kGeoSlots];
   double roots[kGeoSlots][3];
 };
 struct DecideList {
   int n;
-  int slot[kGeoSlots];
+  int slot[kGeoSlots], seq[kGeoSlots];
 };
 
 struct GeoBatchDev {
@@ -464,6 +464,9 @@ geo_eval_kernel(GeoBatchDev B, EvalList L) {
   }
 }
 
+struct WarpScratch;
+__device__ __forceinline__ void decide_slot(const GeoBatchDev& B, int slot, int seq, WarpScratch& ws, int lane);
+
 // The same iterations again with the roots the host's C library computed for their cubics: bit-identical to the reference.
 __global__ void __launch_bounds__(32)
 geo_exact_kernel(GeoBatchDev B, ExactList L) {
@@ -483,6 +486,8 @@ geo_exact_kernel(GeoBatchDev B, ExactList L) {
   __syncwarp();
   const IterRes r = evaluate_models_warp(B, P, ws.F, ws.le, ws.li, nr, V.ge, V.gi, lane);
   if (lane == 0) { V.res[it] = r; V.exact[it] = 1; }
+  __syncwarp();
+  decide_slot(B, L.slot[k], L.seq[k], ws, lane);   // the decision that was waiting for this model, in the same launch
 }
 
 // The accounting warp's view of the evaluated results (warp-parallel searches; every lane returns the same value).
@@ -533,13 +538,18 @@ __device__ __forceinline__ int first_candidate(const SlotView& V, int lo, int hi
 // ------------------------------------------------------------------------------------------ accounting (one warp per slot)
 // The range of the slot's `round` has been evaluated: ask for exact roots where a decision needs them, else account for
 // the range (ac_account), materialise a new sampling set or the final inliers, and tell the host what comes next.
-__global__ void __launch_bounds__(32)
-geo_decide_kernel(GeoBatchDev B, DecideList L) {
-  __shared__ WarpScratch ws;
-  const int lane = threadIdx.x;
-  const SlotView V = slot_view(B, L.slot[blockIdx.x]);
+__device__ __forceinline__ void publish_verdict(DecideOut* dst, const DecideOut& D, int seq) {
+  dst->status = D.status; dst->it = D.it; dst->iters_final = D.iters_final;
+  dst->P[0] = D.P[0]; dst->P[1] = D.P[1]; dst->P[2] = D.P[2]; dst->P[3] = D.P[3];
+  dst->next = D.next;
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(&dst->seq) = seq;
+}
+
+__device__ __forceinline__ void decide_slot(const GeoBatchDev& B, int slot, int seq, WarpScratch& ws, int lane) {
+  const SlotView V = slot_view(B, slot);
   DecideOut D;
-  D.status = 0; D.it = 0; D.iters_final = -1; D.pad = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
+  D.status = 0; D.it = 0; D.iters_final = -1; D.seq = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
   const RoundInfo R = *V.round;
   const GeoPairDev P = B.pairs[R.pair];
   AcState S = *V.state;
@@ -583,7 +593,7 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
       D.next = R;
       if (S.reserve == 0) D.iters_final = S.iter_num;
       else if (no_trigger_in_phase_one) D.iters_final = S.iter_num + S.reserve;
-      if (lane == 0) *V.decide = D;
+      if (lane == 0) publish_verdict(V.decide, D, seq);
       return;
     }
   }
@@ -614,7 +624,13 @@ geo_decide_kernel(GeoBatchDev B, DecideList L) {
   // the loop bound is final once the reserve has been spent (or, with nothing found so far, when the extension is fixed)
   if (S.done || S.reserve == 0) D.iters_final = S.iter_num;
   else if (S.extend_to > 0) D.iters_final = S.extend_to;
-  if (lane == 0) { *V.state = S; *V.round = N; *V.decide = D; }
+  if (lane == 0) { *V.state = S; *V.round = N; publish_verdict(V.decide, D, seq); }
+}
+
+__global__ void __launch_bounds__(32)
+geo_decide_kernel(GeoBatchDev B, DecideList L) {
+  __shared__ WarpScratch ws;
+  decide_slot(B, L.slot[blockIdx.x], L.seq[blockIdx.x], ws, threadIdx.x);
 }
 
 // Filtered matches of the batch: pair p keeps putative[out_idx[k]] for k < out_count[p], in that (residual) order

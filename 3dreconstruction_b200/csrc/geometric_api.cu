@@ -11,6 +11,7 @@
 #include <map>
 #include <new>
 #include <algorithm>
+#include <atomic>
 #include <deque>
 #include <vector>
 
@@ -39,7 +40,6 @@ struct GeoState {
   DevBuf<int> d_vec_index, d_gi, d_out_idx, d_out_count, d_out_iters, d_exact;
   DevBuf<RoundInfo> d_round;
   DevBuf<AcState> d_state;
-  DevBuf<DecideOut> d_decide;
   PinnedBuf<DecideOut> h_decide;
   DevBuf<long long> d_offsets;
   PinnedBuf<GeoPairDev> h_pairs;
@@ -60,7 +60,6 @@ struct GeoState {
   std::map<int, int> logc_off;  // n -> offset in the pool
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_prep = nullptr;
   cudaStream_t slot_stream[kGeoSlots] = {};   // every pair in flight advances on its own stream
-  cudaEvent_t slot_ev[kGeoSlots] = {};
 };
 
 void geo_free(void* p) {
@@ -69,7 +68,7 @@ void geo_free(void* p) {
   G->d_pairs.release(); G->d_matches.release(); G->d_out.release(); G->d_x1.release(); G->d_x2.release();
   G->d_logc_pool.release(); G->d_logc_k.release(); G->d_stream.release(); G->d_res.release(); G->d_models.release(); G->d_ge.release();
   G->d_vec_index.release(); G->d_gi.release(); G->d_out_idx.release(); G->d_out_count.release(); G->d_out_iters.release();
-  G->d_round.release(); G->d_state.release(); G->d_decide.release(); G->h_decide.release(); G->d_basis.release(); G->d_exact.release();
+  G->d_round.release(); G->d_state.release(); G->h_decide.release(); G->d_basis.release(); G->d_exact.release();
   G->d_offsets.release(); G->h_state.release(); G->h_round.release();
   G->h_pairs.release(); G->h_matches.release(); G->h_stream.release(); G->h_out_count.release(); G->h_out_iters.release();
   G->h_offsets.release(); G->r_counts.release(); G->r_offsets.release(); G->r_matches.release();
@@ -77,7 +76,6 @@ void geo_free(void* p) {
   if (G->ev1) cudaEventDestroy(G->ev1);
   if (G->ev_prep) cudaEventDestroy(G->ev_prep);
   for (int q = 0; q < kGeoSlots; ++q) {
-    if (G->slot_ev[q]) cudaEventDestroy(G->slot_ev[q]);
     if (G->slot_stream[q]) cudaStreamDestroy(G->slot_stream[q]);
   }
   delete G;
@@ -126,7 +124,6 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, cudaEventCreateWithFlags(&G.ev_prep, cudaEventDisableTiming));
     for (int q = 0; q < kGeoSlots; ++q) {
       GEO_CHECK(ctx, cudaStreamCreateWithFlags(&G.slot_stream[q], cudaStreamNonBlocking));
-      GEO_CHECK(ctx, cudaEventCreateWithFlags(&G.slot_ev[q], cudaEventDisableTiming));
     }
   }
   cudaStream_t st = V.stream;
@@ -200,7 +197,6 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, G.d_gi.reserve((size_t)(kGeoSlots + max_wave_warps) * n_cap));
     GEO_CHECK(ctx, G.d_round.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.d_state.reserve(kGeoSlots));
-    GEO_CHECK(ctx, G.d_decide.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_decide.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_state.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_round.reserve(kGeoSlots));
@@ -294,7 +290,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     B.logc_pool = G.d_logc_pool.p; B.logc_k = G.d_logc_k.p; B.stream = G.d_stream.p; B.stream_base = offset;
     B.max_iterations = iterations; B.model = model == 'f' ? 0 : 1; B.sample = sample; B.mult_error = model == 'f' ? 0.5 : 1.0; B.it_stride = it_stride; B.n_max = n_max; B.n_cap = n_cap;
     B.res = G.d_res.p; B.models = G.d_models.p; B.basis = G.d_basis.p; B.exact = G.d_exact.p; B.vec_index = G.d_vec_index.p;
-    B.state = G.d_state.p; B.round = G.d_round.p; B.decide = G.d_decide.p; B.g_e = G.d_ge.p; B.g_i = G.d_gi.p;
+    B.state = G.d_state.p; B.round = G.d_round.p; B.decide = G.h_decide.p /* page-locked host memory (unified addressing): the verdicts are polled, not copied */; B.g_e = G.d_ge.p; B.g_i = G.d_gi.p;
     B.out_idx = G.d_out_idx.p; B.out_count = G.d_out_count.p; B.out_iters = G.d_out_iters.p;
     geo_prep_kernel<<<nb, 256, 0, st>>>(B);
     GEO_CHECK(ctx, cudaGetLastError());
@@ -313,9 +309,11 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     // started after it is restarted from the corrected offset.  A speculative pair that finishes early is held in its slot
     // until its offset is confirmed.  Pairs with geometry end the streak and the chain goes back to one start at a time.
     enum { kFree = 0, kNeedEval = 1, kNeedExact = 2, kHeldDone = 3 };
-    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; bool in_flight = false, discard = false; };
+    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; bool in_flight = false, discard = false; int seq = 0; int idle_polls = 0; };
     HostSlot slots[kGeoSlots];
     int next_admit = 0, done_pairs = 0;
+    for (int q = 0; q < kGeoSlots; ++q) G.h_decide.p[q].seq = 0;
+    int launch_seq = 0;
     std::deque<int> chain;          // slots of the pairs in flight whose iteration count is still open, oldest first; only
                                     // the front one has a definite offset, the others were started speculatively
     long long chain_offset = offset;  // offset of the next pair when the chain is empty
@@ -356,12 +354,14 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         ++next_admit;
       }
       // launches: every slot with something to do and nothing in flight gets, on ITS stream, the evaluation of its
-      // pending range (or the re-evaluation of one iteration with roots from this machine's C library), its accounting
-      // warp and the copy of the verdict; the slots advance independently of each other
+      // pending range followed by its accounting warp -- or, in one launch, the re-evaluation of one iteration with roots
+      // from this machine's C library and the accounting that was waiting for it.  The accounting warp stores its verdict
+      // straight into page-locked host memory, sequence number last; the host polls that number: no copy, no event
       for (int q = 0; q < kGeoSlots; ++q) {
         HostSlot& H = slots[q];
         if (H.in_flight || (H.state != kNeedEval && H.state != kNeedExact)) continue;
         cudaStream_t sq = G.slot_stream[q];
+        H.seq = ++launch_seq;
         if (H.state == kNeedEval) {
           EvalList EL;
           EL.n = 1; EL.slot[0] = q; EL.first_warp[0] = 0;
@@ -376,40 +376,39 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
             GEO_CHECK(ctx, cudaGetLastError());
             ++launches;
           }
+          DecideList DL;
+          DL.n = 1; DL.slot[0] = q; DL.seq[0] = H.seq;
+          geo_decide_kernel<<<1, 32, 0, sq>>>(B, DL);
+          GEO_CHECK(ctx, cudaGetLastError());
+          ++launches;
         } else {
           ExactList XL;
-          XL.n = 1; XL.slot[0] = q; XL.it[0] = H.it;
+          XL.n = 1; XL.slot[0] = q; XL.it[0] = H.it; XL.seq[0] = H.seq;
           XL.nr[0] = solve_cubic(H.P, XL.roots[0]);  // host libm: acos / cos / pow as the reference's process would call them
           geo_exact_kernel<<<1, 32, 0, sq>>>(B, XL);
           GEO_CHECK(ctx, cudaGetLastError());
           ++launches;
           ++exact_requests;
         }
-        DecideList DL;
-        DL.n = 1; DL.slot[0] = q;
-        geo_decide_kernel<<<1, 32, 0, sq>>>(B, DL);
-        GEO_CHECK(ctx, cudaGetLastError());
-        ++launches;
         ++waves;
-        GEO_CHECK(ctx, cudaMemcpyAsync(G.h_decide.p + q, G.d_decide.p + q, sizeof(DecideOut), cudaMemcpyDeviceToHost, sq));
-        GEO_CHECK(ctx, cudaEventRecord(G.slot_ev[q], sq));
         H.in_flight = true;
       }
       // wait until at least one slot has its verdict, then take every verdict that is there
       int completed = 0;
+      long long spins = 0;
       while (!completed) {
         bool any_in_flight = false;
         for (int q = 0; q < kGeoSlots; ++q) {
           HostSlot& H = slots[q];
           if (!H.in_flight) continue;
           any_in_flight = true;
-          const cudaError_t qe = cudaEventQuery(G.slot_ev[q]);
-          if (qe == cudaErrorNotReady) continue;
-          GEO_CHECK(ctx, qe);
+          const volatile DecideOut* hv = G.h_decide.p + q;
+          if (hv->seq != H.seq) continue;
+          std::atomic_thread_fence(std::memory_order_acquire);
           H.in_flight = false;
           ++completed;
           if (H.discard) { H.discard = false; continue; }   // the verdict of a refuted start
-          const DecideOut& D = G.h_decide.p[q];
+          const DecideOut D = *const_cast<const DecideOut*>(G.h_decide.p + q);
           if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
           if (D.status == 1) {
             H.state = kNeedExact; H.it = D.it;
@@ -427,6 +426,16 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
           }
         }
         if (!any_in_flight) return fail(ctx, "geometric_filter: internal error (no pair in flight)");
+        if (!completed && (++spins & 0xffff) == 0) {
+          // nothing for a while: a failed launch would never publish -- ask the streams
+          for (int q = 0; q < kGeoSlots; ++q) {
+            if (!slots[q].in_flight) continue;
+            const cudaError_t qe = cudaStreamQuery(G.slot_stream[q]);
+            if (qe != cudaSuccess && qe != cudaErrorNotReady) GEO_CHECK(ctx, qe);
+            if (qe == cudaSuccess && (G.h_decide.p + q)->seq != slots[q].seq && (++slots[q].idle_polls > 2))
+              return fail(ctx, "geometric_filter: internal error (a slot's launches ended without a verdict)");
+          }
+        }
       }
       // the chain: a front pair whose count is final leaves it and confirms or refutes the offset of the next one
       while (!chain.empty() && slots[chain.front()].iters_final >= 0) {
@@ -450,6 +459,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
         break;
       }
     }
+    for (int q = 0; q < kGeoSlots; ++q) GEO_CHECK(ctx, cudaStreamSynchronize(G.slot_stream[q]));  // (idle by now: the verdicts are in)
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_count.p, G.d_out_count.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_iters.p, G.d_out_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaStreamSynchronize(st));
