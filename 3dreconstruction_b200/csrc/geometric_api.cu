@@ -268,21 +268,22 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       }
       mo += D.n;
     }
-    // stream window [offset, offset + 7 * iterations * nb)
+    // stream window [offset, offset + sample * iterations * nb): room for the whole batch, but the values are GENERATED as
+    // the pairs are started (start_pair below: 28,672 values = ~90 us of host time per pair, beside the GPU's work instead
+    // of in front of it) and each pair uploads its own range on its own stream.  Values generated for the previous batch
+    // and not consumed by it are carried over.
     const long long need_end = offset + (long long)sample * iterations * nb;
-    if (offset > win_base) {
-      window.erase(window.begin(), window.begin() + (size_t)(offset - win_base));
-      win_base = offset;
-    }
-    window.reserve((size_t)(need_end - win_base));
-    while (gen_pos < need_end) { window.push_back(glibc_rand(gen)); ++gen_pos; }
     const size_t n_stream = (size_t)(need_end - offset);
     GEO_CHECK(ctx, G.h_stream.reserve(n_stream));
     GEO_CHECK(ctx, G.d_stream.reserve(n_stream));
-    memcpy(G.h_stream.p, window.data() + (size_t)(offset - win_base), n_stream * sizeof(uint32_t));
+    if (offset > win_base) {
+      window.erase(window.begin(), window.begin() + (size_t)std::min<long long>(offset - win_base, (long long)window.size()));
+      win_base = offset;
+    }
+    if (!window.empty()) memcpy(G.h_stream.p, window.data(), std::min(window.size(), n_stream) * sizeof(uint32_t));
+    const long long batch_base = offset;
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_pairs.p, G.h_pairs.p, nb * sizeof(GeoPairDev), cudaMemcpyHostToDevice, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_matches.p, G.h_matches.p, tot * sizeof(int2), cudaMemcpyHostToDevice, st));
-    GEO_CHECK(ctx, cudaMemcpyAsync(G.d_stream.p, G.h_stream.p, n_stream * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     GEO_CHECK(ctx, cudaEventRecord(G.ev0, st));
 
     GeoBatchDev B;
@@ -331,6 +332,12 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       G.h_state.p[sl] = S0;
       G.h_round.p[sl] = R0;
       GEO_CHECK(ctx, cudaStreamWaitEvent(G.slot_stream[sl], G.ev_prep, 0));  // the batch's points are normalised
+      {  // the pair's part of the rand() stream: generated up to its end if it is not yet, uploaded on the pair's stream
+        const long long end = off + (long long)sample * iterations;
+        while (gen_pos < end) { G.h_stream.p[gen_pos - batch_base] = glibc_rand(gen); ++gen_pos; }
+        GEO_CHECK(ctx, cudaMemcpyAsync(G.d_stream.p + (off - batch_base), G.h_stream.p + (off - batch_base),
+                                       (size_t)sample * iterations * sizeof(uint32_t), cudaMemcpyHostToDevice, G.slot_stream[sl]));
+      }
       GEO_CHECK(ctx, cudaMemcpyAsync(G.d_state.p + sl, G.h_state.p + sl, sizeof(AcState), cudaMemcpyHostToDevice, G.slot_stream[sl]));
       GEO_CHECK(ctx, cudaMemcpyAsync(G.d_round.p + sl, G.h_round.p + sl, sizeof(RoundInfo), cudaMemcpyHostToDevice, G.slot_stream[sl]));
       HostSlot& H = slots[sl];
@@ -464,6 +471,9 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_iters.p, G.d_out_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaStreamSynchronize(st));
     const long long offset_after = chain_offset;
+    // values generated beyond what the batch consumed belong to the next batch (or stay unused after the last one)
+    window.assign(G.h_stream.p + (offset_after - batch_base), G.h_stream.p + (gen_pos - batch_base));
+    win_base = offset_after;
     long long kept_total = 0;
     for (int k = 0; k < nb; ++k) { G.h_offsets.p[k] = kept_total; kept_total += G.h_out_count.p[k]; }
     G.h_offsets.p[nb] = kept_total;
