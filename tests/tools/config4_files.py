@@ -4,6 +4,7 @@ match + format / export) and the sha256 + size of matches.putative.txt.  With CH
 again on one GPU and the two files must be byte-identical.  Log kept under profiles/.
 
     NIMG=1000 ROWS=8000 GPUS=8 python tests/tools/config4_files.py
+    NIMG=350 ROWS=8000 GPUS=1 GEO=f python tests/tools/config4_files.py     (putative stage + AC-RANSAC filter stage)
 """
 import hashlib, importlib, multiprocessing as mp, os, shutil, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,6 +12,7 @@ sys.path.insert(0, ROOT)
 EXE = os.path.join(ROOT, "build", "compute_matches")
 N = int(os.environ.get("NIMG", "1000")); ROWS = int(os.environ.get("ROWS", "8000")); GPUS = os.environ.get("GPUS", "8")
 CFG = 4
+GEO = os.environ.get("GEO", "")   # "f" / "h": run the geometric filter stage too (compute_matches -g f)
 _pool = None
 
 
@@ -32,7 +34,7 @@ def run(td, gpus):
     if os.path.exists(out):
         os.remove(out)
     t0 = time.time()
-    r = subprocess.run([EXE, "-i", td, "-o", td, "-r", "0.8", "--gpus", str(gpus)], capture_output=True, text=True, timeout=1200)
+    r = subprocess.run([EXE, "-i", td, "-o", td, "-r", "0.8", "--gpus", str(gpus)] + (["-g", GEO] if GEO else []), capture_output=True, text=True, timeout=2400)
     wall = time.time() - t0
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:], flush=True)
@@ -43,6 +45,9 @@ def run(td, gpus):
         for blk in iter(lambda: f.read(1 << 24), b""):
             h.update(blk)
     print(f"[--gpus {gpus}] wall {wall:.2f} s (process start to exit); {line}; file {os.path.getsize(out) / 1e6:.1f} MB sha256 {h.hexdigest()[:16]}", flush=True)
+    for l in r.stdout.splitlines():
+        if l.startswith("geometric filter ("):
+            print("   " + l, flush=True)
     return h.hexdigest()
 
 
