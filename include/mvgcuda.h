@@ -221,7 +221,12 @@ int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* p
  * A pair may hold at most 16,384 putative matches (MVGCUDA_ERR_INVALID beyond).
  * The feature coordinates must have been set (mvgcuda_set_features / mvgcuda_stream_image).  The result (matches of every
  * pair in ascending-residual order, as the reference stores them) is owned by the context and valid until the next
- * geometric_filter / destroy; out->rescanned_queries holds the number of rand() values consumed. */
+ * geometric_filter / destroy; out->rescanned_queries holds the number of rand() values consumed,
+ * out->knn_kernel_launches the number of models re-evaluated with roots from the host's C library.
+ * Scheduling (pairs in flight on their own streams, pairs started ahead on the assumption that their predecessors find no
+ * model) never shows in the result: a start that turns out to be wrong is repeated from the right rand() offset.  The
+ * calling thread polls page-locked memory while the GPU works.  MVGCUDA_GEO_STATS=1 in the environment prints one line of
+ * counters per call to stderr (launches, re-evaluated models, refuted starts, rand() position). */
 int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double precision, int iterations, unsigned seed,
                              int64_t n_pairs, const int32_t* pairs, const int32_t* counts, const int64_t* offsets,
                              const int32_t* matches, const int32_t* image_sizes, mvgcuda_pair_matches* out);
