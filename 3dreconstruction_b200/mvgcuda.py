@@ -136,13 +136,27 @@ def pairs_exhaustive(n_images: int) -> np.ndarray:
     return np.stack([i, j], axis=1).astype(np.int32)
 
 
-def upload_friendly_order(pairs: np.ndarray) -> np.ndarray:
-    """The same pairs, ordered by their LARGER image id first (then the smaller): with images streamed in index order the
-    first batches only touch images that have already arrived, so matching overlaps the rest of the upload.  Results are
-    keyed by pair, so the order is free (the export sorts by (i, j) itself)."""
+def upload_friendly_order(pairs: np.ndarray, head_images: Optional[int] = None) -> np.ndarray:
+    """The same pairs in an order that lets matching overlap a streamed upload AND keeps the fused kernel fed:
+      * head: the pairs among the first `head_images` images (default: a third of them, at least 8), by their LARGER image
+        id first -- with images streamed in index order these batches only touch images that have already arrived;
+      * tail: everything else in (i, j) order, as the reference visits them.  Consecutive pairs then share their db image
+        I, whose tiles stay in L2; in larger-id-first order the db image changes with every pair and every pair starts
+        with a cold fetch of its first db tiles (measured on a resident collection of 100 x 10k: 45.2 instead of 42.4 ms
+        in the fused kernel).  By the time the head has been matched the rest of the upload has arrived (end to end, 100
+        images x 10k: head 16 / 25 / 34 / 50 / all = 105 / 106 / 110 / 108 / 104k pairs/s).
+    Results are keyed by pair, so the order is free (the export sorts by (i, j) itself)."""
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    if len(pairs) == 0:
+        return pairs
     hi, lo = pairs.max(axis=1), pairs.min(axis=1)
-    return pairs[np.lexsort((lo, hi))]
+    n = int(hi.max()) + 1
+    m = int(head_images) if head_images is not None else max(8, (n + 2) // 3)
+    head = hi < m
+    hp, tp = pairs[head], pairs[~head]
+    hp = hp[np.lexsort((lo[head], hi[head]))]
+    tp = tp[np.lexsort((tp[:, 1], tp[:, 0]))]
+    return np.ascontiguousarray(np.concatenate([hp, tp]))
 
 
 def write_matches(path: str, res: "PairMatches", skip_empty: bool = False) -> None:

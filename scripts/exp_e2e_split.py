@@ -12,7 +12,8 @@ pf = [torch.empty((rows, 2), dtype=torch.float32).pin_memory() for _ in range(n_
 for k in range(n_img):
     pd[k].numpy()[:] = descs0[k]; pf[k].numpy()[:] = synth.features(3, k, rows)[:, :2]
 descs = [t.numpy() for t in pd]; feats = [t.numpy() for t in pf]
-pairs = pkg.upload_friendly_order(pkg.pairs_exhaustive(n_img))
+head = os.environ.get('HEAD')
+pairs = pkg.upload_friendly_order(pkg.pairs_exhaustive(n_img), int(head) if head else None)
 rs = float(pkg.square_f32(0.8))
 ctx = pkg.Context(0)
 m = pkg.MatcherCudaAllInMemory(0.8, ctx)
