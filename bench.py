@@ -387,8 +387,9 @@ def run_ours(args):
 
     # ---------------- e2e: host buffers -> public collection API -> matches on the host, every step.  Every rank reads
     # the collection over its own PCIe link (pinned staging, one asynchronous copy per image) -- no collective at all.
-    # The images travel in the order the rank's pairs first need them, the pairs are visited larger-image-id first, and the
-    # match call starts while later images are still on the wire (batches wait only for the images they touch).
+    # The images travel in the order the rank's pairs first need them, the pairs of the first third of the images are
+    # visited larger-image-id first and the rest in (i, j) order (upload_friendly_order), and the match call starts while
+    # later images are still on the wire (batches wait only for the images they touch).
     matcher = pkg.MatcherCudaAllInMemory(RATIO, ctx)
     e2e_pairs = pkg.upload_friendly_order(my_pairs)
     seen, upload_order = set(), []
