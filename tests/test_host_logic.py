@@ -132,3 +132,25 @@ def test_rbtree_dedup_restatement_matches_std_set(tmp_path):
     r = subprocess.run([str(exe), "8000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rbtree_dedup == std::set" in r.stdout
+
+
+def test_upload_friendly_order_is_a_permutation_with_a_streamable_head():
+    """The pair order of the streamed path: same pairs; the head (pairs among the first third of the images) by larger image
+    id, so that batch k only touches images 0..k; the tail in the reference's (i, j) order (db image constant over runs)."""
+    import importlib
+    pkg = importlib.import_module("3dreconstruction_b200")
+    for n in (2, 9, 30, 100):
+        pairs = pkg.pairs_exhaustive(n)
+        got = pkg.upload_friendly_order(pairs)
+        assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, pairs.tolist()))
+        m = max(8, (n + 2) // 3)
+        head = [p for p in got.tolist() if max(p) < m]
+        tail = [p for p in got.tolist() if max(p) >= m]
+        assert got.tolist() == head + tail
+        assert [max(p) for p in head] == sorted(max(p) for p in head)
+        assert tail == sorted(tail)
+    # a shard of the list (one rank's contiguous chunk) and an explicit head size
+    shard = pkg.pairs_exhaustive(50)[300:700]
+    got = pkg.upload_friendly_order(shard, head_images=20)
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, shard.tolist()))
+    assert len(pkg.upload_friendly_order(np.zeros((0, 2), np.int32))) == 0
