@@ -63,3 +63,27 @@ def test_compute_matches_geometric_stage_golden(pkg, et, tmp_path):
     # the essential model (the reference's default, needs K.txt) stops after the putative stage
     out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.6", "-g", "e"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "only -g f and -g h" in out.stdout and not (tmp_path / "matches.e.txt").exists()
+
+
+@pytest.mark.parametrize("name", ["sceaux", "ace"])
+def test_compute_matches_on_the_bundled_image_pairs(pkg, tmp_path, name):
+    """BASELINE configs[0] end to end through the driver: the reference's SIFT regions of a bundled data/imageData pair as
+    .feat/.desc files + lists.txt with the real image sizes -> `compute_matches -r 0.8 -g f` and `-g h`: matches.putative.txt,
+    matches.f.txt and matches.h.txt byte-identical to the reference's two stages (goldens: make_golden_imagedata.py,
+    make_golden_geometric_imagedata.py)."""
+    import json
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, "imagedata_collection.npz"))
+    g = np.load(os.path.join(GOLDEN, "imagedata_geometric.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "imagedata_geometric_golden.json")))[name]
+    lines = []
+    for k in range(2):
+        pkg.io.save_descs_bin(str(tmp_path / f"im{k}.desc"), z[f"{name}_desc_{k}"], 8)
+        pkg.io.save_feats(str(tmp_path / f"im{k}.feat"), z[f"{name}_feat_{k}"])
+        lines.append(f"im{k}.jpg;{meta['sizes'][k][0]};{meta['sizes'][k][1]}\n")
+    (tmp_path / "lists.txt").write_text("".join(lines))
+    for model in ("f", "h"):
+        out = subprocess.run([EXE, "-i", str(tmp_path), "-o", str(tmp_path), "-r", "0.8", "-g", model, "--gpus", "1"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr + out.stdout
+        assert (tmp_path / "matches.putative.txt").read_bytes() == z[f"{name}_text_r0.8"].tobytes()
+        assert (tmp_path / f"matches.{model}.txt").read_bytes() == g[f"{name}_r0.8_{model}"].tobytes()
