@@ -439,7 +439,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
             if (!slots[q].in_flight) continue;
             const cudaError_t qe = cudaStreamQuery(G.slot_stream[q]);
             if (qe != cudaSuccess && qe != cudaErrorNotReady) GEO_CHECK(ctx, qe);
-            if (qe == cudaSuccess && (G.h_decide.p + q)->seq != slots[q].seq && (++slots[q].idle_polls > 2))
+            if (qe == cudaSuccess && static_cast<const volatile DecideOut*>(G.h_decide.p + q)->seq != slots[q].seq && (++slots[q].idle_polls > 2))
               return fail(ctx, "geometric_filter: internal error (a slot's launches ended without a verdict)");
           }
         }
