@@ -1,20 +1,24 @@
-// acransac_kernels.cuh -- AC-RANSAC fundamental-matrix filter on the GPU (replaces
-// ImageCollectionGeometricFilter::Filter + GeometricFilter_FMatrix_AC, geometric_filter.h:37-102, fundamental_acransac.h:13-57,
-// estimator_acransac.h:125-245).  Compiled with -fmad=false (see acransac_core.cuh).
+// acransac_kernels.cuh -- AC-RANSAC geometric filter on the GPU, fundamental-matrix and homography models (SURVEY.md
+// 8(f)-1; replaces ImageCollectionGeometricFilter::Filter + GeometricFilter_FMatrix_AC / GeometricFilter_HMatrix_AC,
+// geometric_filter.h:37-102, fundamental_acransac.h:13-57, homography_acransac.h:18-62, estimator_acransac.h:125-245).
+// Compiled with -fmad=false (see acransac_core.cuh).
 //
-// The reference's results are defined by ONE global rand() stream consumed pair after pair (7 values per iteration, the
-// iteration count of a pair depends on when its first meaningful model turns up), so pairs form a chain: a pair's stream
-// offset is known only when the previous pair's first phase is over.  The pairs are therefore walked in order and the
-// parallelism comes from INSIDE a pair: all iterations of the current range are evaluated at once, one warp each
-// (geo_eval_kernel: sample, 7-point solve -- lane 0: 9x9 Jacobi SVD bit-faithful to Eigen + cubic --, then per model all
-// residuals with the lanes over the points, ordered ballot compaction of the candidates <= max_threshold, bitonic sort
-// in shared memory (global scratch for long lists), parallel NFA scan), and ONE warp accounts for them in order
-// (geo_decide_kernel, acransac_engine.cuh).
+// The reference's results are defined by ONE global rand() stream consumed pair after pair (7 or 4 values per iteration;
+// the iteration count of a pair depends on when its first meaningful model turns up), so pairs form a chain: a pair's
+// stream offset is known only when the previous pair's iteration count is final.  Only the STARTS of the pairs are
+// ordered by that chain (geometric_api.cu: up to kGeoSlots pairs in flight, each on its own stream, some started ahead
+// speculatively); the parallelism inside a pair comes from evaluating whole RANGES of iterations at once
+// (geo_eval_kernel: sample, solve -- 9x9 Jacobi SVD bit-faithful to Eigen, three iterations side by side per warp, + cubic
+// or QR preconditioner --, then per model all residuals with the lanes over the points, ordered ballot compaction of the
+// candidates <= max_threshold, bitonic sort in shared memory (global scratch for long lists; the reference's std::sort
+// restated step by step when a residual is NaN), parallel NFA scan), after which ONE warp accounts for them in order
+// (decide_slot, acransac_engine.cuh) and writes its verdict into page-locked host memory.
 // Exactness: the evaluation uses CUDA's acos / cos / pow for the cubic, which differ from the host C library's in the last
 // bit of ~10 % of the roots; a model an ACRANSAC decision hinges on (a trigger, the best model at the end of the first
 // phase, and anything within a guard band of those thresholds) is re-evaluated from the same null vectors with the roots
 // the HOST's libm gives for its cubic (geo_exact_kernel) before the decision is taken, so accepted models -- and with them
-// the sampling sets, the inlier lists and their order -- carry the reference's bits.
+// the sampling sets, the inlier lists and their order -- carry the reference's bits.  The homography model has no
+// transcendental function: every bit is the device's own.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -62,7 +66,7 @@ struct DecideOut {   // the accounting warp's verdict, per slot: written straigh
 // after the predecessor's first accepted model -- so the later rounds of a pair run beside the first rounds of the next.
 constexpr int kGeoSlots = 16;
 
-struct EvalList {    // one wave of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1])
+struct EvalList {    // one launch of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1]) (the host sends one slot per launch)
   int n;
   int group;         // iterations a warp takes: kEvalGroup when the range is wide (throughput), 1 when it is narrow (latency)
   int scratch_base;  // first warp-scratch list of this launch (launches of different slots run side by side)
@@ -105,7 +109,7 @@ struct GeoBatchDev {
   AcState* state;           // [slots]
   RoundInfo* round;         // [slots]
   DecideOut* decide;        // [slots]
-  double* g_e;              // long candidate lists: [slots (accounting / exact warps) + warps of an evaluation wave][n_cap]
+  double* g_e;              // long candidate lists: [slots (accounting / exact warps) + slots x warps of a range evaluation][n_cap]
   int* g_i;
   int* out_idx;             // [matches of the batch]: inlier positions (into the pair's putative list), in residual order
   int* out_count;           // [n_pairs]
@@ -281,7 +285,7 @@ __device__ __forceinline__ IterRes evaluate_models_warp(const GeoBatchDev& B, co
 // A warp takes kEvalGroup consecutive iterations of [round.lo, round.hi) of a slot (estimator_acransac.h:166-218).
 //   solve:     the Jacobi SVD is a chain of ~250 dependent 2x2 steps (six fp64 divisions and three square roots each) in
 //              which nine lanes at most have element pairs to rotate -- the fp64 pipe, which a warp instruction occupies
-//              whatever its active lanes, is what a wave of evaluations runs out of.  So THREE iterations are solved side
+//              whatever its active lanes, is what a GPU full of evaluations runs out of.  So THREE iterations are solved side
 //              by side, lanes 10 g .. 10 g + 8 on the matrices of iteration g: one instruction stream, every lane computes
 //              the 2x2 step of its own group, a step is skipped only when no group needs it (a converged matrix asks for
 //              nothing more, exactly as its own loop would have ended).  Per element exactly the scalar operations.

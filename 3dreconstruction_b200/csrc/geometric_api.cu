@@ -148,7 +148,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       n_max = std::max(n_max, counts[p]);
     }
   }
-  // every warp of an evaluation wave owns a candidate list of n_cap entries in global scratch (used when more than 256
+  // every warp of a range evaluation owns a candidate list of n_cap entries in global scratch (used when more than 256
   // residuals lie under the threshold): bounded so that the scratch stays below ~1.5 GB
   if (n_max > kGeoMaxMatchesPerPair) return fail(ctx, "geometric_filter: a pair with more than 16,384 putative matches is not supported");
   GEO_CHECK(ctx, G.r_counts.reserve(std::max<int64_t>(n_pairs, 1)));
@@ -179,29 +179,29 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     GEO_CHECK(ctx, cudaMemcpyAsync(G.d_logc_pool.p, G.logc_pool.data(), G.logc_pool.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   }
 
-  // ---- scratch: kGeoSlots pairs in flight, each with its per-iteration arrays; one warp per iteration of a wave
+  // ---- scratch: kGeoSlots pairs in flight, each with its per-iteration arrays and its region of warp-scratch lists
   int n_cap = 32;
   while (n_cap < n_max) n_cap <<= 1;
   const int it_stride = iterations + 8;
   // warps of one range evaluation (one iteration per warp in a narrow range, kEvalGroup in a wide one); every slot has its
   // own region of warp-scratch lists, so that the launches of different slots can run side by side
   const int slot_warps = ((std::max(std::min(iterations, kNarrowRangeIterations), iterations / kEvalGroup + 1) + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
-  const int max_wave_warps = kGeoSlots * slot_warps;
+  const int scratch_warps = kGeoSlots * slot_warps;
   if (!active.empty()) {
     GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
     GEO_CHECK(ctx, G.d_basis.reserve((size_t)kGeoSlots * it_stride * kBasisDoubles));
     GEO_CHECK(ctx, G.d_exact.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_vec_index.reserve((size_t)kGeoSlots * n_max));
-    GEO_CHECK(ctx, G.d_ge.reserve((size_t)(kGeoSlots + max_wave_warps) * n_cap));
-    GEO_CHECK(ctx, G.d_gi.reserve((size_t)(kGeoSlots + max_wave_warps) * n_cap));
+    GEO_CHECK(ctx, G.d_ge.reserve((size_t)(kGeoSlots + scratch_warps) * n_cap));
+    GEO_CHECK(ctx, G.d_gi.reserve((size_t)(kGeoSlots + scratch_warps) * n_cap));
     GEO_CHECK(ctx, G.d_round.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.d_state.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_decide.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_state.reserve(kGeoSlots));
     GEO_CHECK(ctx, G.h_round.reserve(kGeoSlots));
   }
-  long long exact_requests = 0, waves = 0, respeculated = 0;
+  long long exact_requests = 0, rounds = 0, respeculated = 0;
 
   // ---- the process-wide rand() stream: srand(seed) here, consumed pair after pair (the reference never seeds: seed 1)
   GlibcRand gen;
@@ -397,7 +397,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
           ++launches;
           ++exact_requests;
         }
-        ++waves;
+        ++rounds;
         H.in_flight = true;
       }
       // wait until at least one slot has its verdict, then take every verdict that is there
@@ -513,8 +513,8 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     if (!kept[a].empty()) memcpy(G.r_matches.p + 2 * G.r_offsets.p[active[a]], kept[a].data(), kept[a].size() * sizeof(int32_t));
   if (const char* v = getenv("MVGCUDA_GEO_STATS"))
     if (*v == '1')
-      fprintf(stderr, "mvgcuda_geometric_filter('%c'): %zu active pairs, %lld waves, %d launches, %lld models re-evaluated with host roots, "
-                      "%lld speculative starts refuted, %lld rand() values\n", model, active.size(), waves, launches, exact_requests, respeculated, offset);
+      fprintf(stderr, "mvgcuda_geometric_filter('%c'): %zu active pairs, %lld rounds, %d launches, %lld models re-evaluated with host roots, "
+                      "%lld speculative starts refuted, %lld rand() values\n", model, active.size(), rounds, launches, exact_requests, respeculated, offset);
   if (out) {
     out->n_pairs = n_pairs;
     out->counts = G.r_counts.p;
