@@ -223,15 +223,16 @@ __device__ __forceinline__ int model_candidates_warp(const GeoBatchDev& B, const
   while (p2 < m) p2 <<= 1;
   for (int k = m + lane; k < p2; k += 32) { le[k] = ac_inf(); li[k] = 0x7fffffff; }
   __syncwarp();
+  // bitonic network; every lane owns compare-exchanges (pair t = the t-th index with bit j clear and its partner), so no
+  // lane idles on the upper element of a pair
   for (int k = 2; k <= p2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int idx = lane; idx < p2; idx += 32) {
-        const int ixj = idx ^ j;
-        if (ixj > idx) {
-          const Cand a{le[idx], li[idx]}, b{le[ixj], li[ixj]};
-          const bool up = (idx & k) == 0;
-          if (up ? cand_less(b, a) : cand_less(a, b)) { le[idx] = b.e; li[idx] = b.i; le[ixj] = a.e; li[ixj] = a.i; }
-        }
+      for (int t = lane; t < (p2 >> 1); t += 32) {
+        const int idx = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = idx | j;
+        const Cand a{le[idx], li[idx]}, b{le[ixj], li[ixj]};
+        const bool up = (idx & k) == 0;
+        if (up ? cand_less(b, a) : cand_less(a, b)) { le[idx] = b.e; li[idx] = b.i; le[ixj] = a.e; li[ixj] = a.i; }
       }
       __syncwarp();
     }
