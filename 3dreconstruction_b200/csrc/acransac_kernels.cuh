@@ -57,6 +57,8 @@ struct DecideOut {   // the accounting warp's verdict, per slot: written straigh
   int it;
   int iters_final;   // >= 0 once the number of iterations the pair will run is known (the next pair's rand() offset follows)
   int seq;           // the launch's sequence number, stored after a system-wide fence: the host polls it
+  int iters_guess;   // status 1 in the first phase: the count if iteration `it` is confirmed as the first trigger (else -1)
+  int pad;
   double P[4];
   RoundInfo next;
 };
@@ -66,21 +68,24 @@ struct DecideOut {   // the accounting warp's verdict, per slot: written straigh
 // after the predecessor's first accepted model -- so the later rounds of a pair run beside the first rounds of the next.
 constexpr int kGeoSlots = 16;
 
-struct EvalList {    // one launch of range evaluations: slot[k] covers warps [first_warp[k], first_warp[k + 1]) (the host sends one slot per launch)
+// Launch arguments.  The host sends ONE slot per launch (every pair in flight has its own stream), so the lists hold a
+// single entry: kernel parameters stay a few dozen bytes.
+constexpr int kListSlots = 1;
+struct EvalList {    // range evaluation: slot[k] covers warps [first_warp[k], first_warp[k + 1])
   int n;
   int group;         // iterations a warp takes: kEvalGroup when the range is wide (throughput), 1 when it is narrow (latency)
   int scratch_base;  // first warp-scratch list of this launch (launches of different slots run side by side)
-  int slot[kGeoSlots];
-  int first_warp[kGeoSlots + 1];
+  int slot[kListSlots];
+  int first_warp[kListSlots + 1];
 };
 struct ExactList {   // iterations to re-evaluate with the host's roots (the accounting follows in the same warp)
   int n;
-  int slot[kGeoSlots], it[kGeoSlots], nr[kGeoSlots], seq[kGeoSlots];
-  double roots[kGeoSlots][3];
+  int slot[kListSlots], it[kListSlots], nr[kListSlots], seq[kListSlots];
+  double roots[kListSlots][3];
 };
 struct DecideList {
   int n;
-  int slot[kGeoSlots], seq[kGeoSlots];
+  int slot[kListSlots], seq[kListSlots];
 };
 
 struct GeoBatchDev {
@@ -544,7 +549,7 @@ __device__ __forceinline__ int first_candidate(const SlotView& V, int lo, int hi
 // The range of the slot's `round` has been evaluated: ask for exact roots where a decision needs them, else account for
 // the range (ac_account), materialise a new sampling set or the final inliers, and tell the host what comes next.
 __device__ __forceinline__ void publish_verdict(DecideOut* dst, const DecideOut& D, int seq) {
-  dst->status = D.status; dst->it = D.it; dst->iters_final = D.iters_final;
+  dst->status = D.status; dst->it = D.it; dst->iters_final = D.iters_final; dst->iters_guess = D.iters_guess;
   dst->P[0] = D.P[0]; dst->P[1] = D.P[1]; dst->P[2] = D.P[2]; dst->P[3] = D.P[3];
   dst->next = D.next;
   __threadfence_system();
@@ -554,7 +559,7 @@ __device__ __forceinline__ void publish_verdict(DecideOut* dst, const DecideOut&
 __device__ __forceinline__ void decide_slot(const GeoBatchDev& B, int slot, int seq, WarpScratch& ws, int lane) {
   const SlotView V = slot_view(B, slot);
   DecideOut D;
-  D.status = 0; D.it = 0; D.iters_final = -1; D.seq = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
+  D.status = 0; D.it = 0; D.iters_final = -1; D.seq = 0; D.iters_guess = -1; D.pad = 0; D.P[0] = D.P[1] = D.P[2] = D.P[3] = 0.0;
   const RoundInfo R = *V.round;
   const GeoPairDev P = B.pairs[R.pair];
   AcState S = *V.state;
@@ -598,6 +603,7 @@ __device__ __forceinline__ void decide_slot(const GeoBatchDev& B, int slot, int 
       D.next = R;
       if (S.reserve == 0) D.iters_final = S.iter_num;
       else if (no_trigger_in_phase_one) D.iters_final = S.iter_num + S.reserve;
+      else if (!ext && need == t) D.iters_guess = t + 1 + S.reserve;   // confirmed, t is the first trigger (:228-234)
       if (lane == 0) publish_verdict(V.decide, D, seq);
       return;
     }

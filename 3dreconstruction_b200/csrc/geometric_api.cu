@@ -186,7 +186,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   // warps of one range evaluation (one iteration per warp in a narrow range, kEvalGroup in a wide one); every slot has its
   // own region of warp-scratch lists, so that the launches of different slots can run side by side
   const int slot_warps = ((std::max(std::min(iterations, kNarrowRangeIterations), iterations / kEvalGroup + 1) + kEvalWarps - 1) / kEvalWarps) * kEvalWarps;
-  const int scratch_warps = kGeoSlots * slot_warps;
+  // pairs in flight: all the slots, fewer when their scratch lists would be huge (pairs with many thousands of matches)
+  int n_slots = kGeoSlots;
+  while (n_slots > 4 && (size_t)n_slots * slot_warps * n_cap * (sizeof(double) + sizeof(int)) > ((size_t)3 << 30)) n_slots >>= 1;
+  const int scratch_warps = n_slots * slot_warps;
   if (!active.empty()) {
     GEO_CHECK(ctx, G.d_res.reserve((size_t)kGeoSlots * it_stride));
     GEO_CHECK(ctx, G.d_models.reserve((size_t)kGeoSlots * it_stride * 27));
@@ -303,14 +306,16 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     // evaluation of its pending range (or the re-evaluation of one iteration with roots from THIS machine's C library),
     // its accounting warp, the copy of the verdict, an event the host polls.  No pair waits for another one's kernels.
     //
-    // Speculative starts: a pair that finds no meaningful model runs exactly `iterations` iterations, and in a large
+    // Speculative starts: (1) a pair whose first trigger candidate waits for its exact roots will, if the candidate is
+    // confirmed (it almost always is), run candidate + 1 + reserve iterations: its successor starts on that guess, one
+    // round early.  (2) A pair that finds no meaningful model runs exactly `iterations` iterations, and in a large
     // exhaustive collection most pairs are of that kind.  After two such pairs in a row up to kSpecDepth FURTHER pairs are
     // started at the offsets that assumption gives (each is an upper bound, so the stream window covers them); when a
     // pair's count becomes final the next one is either confirmed (its offset was right: nothing to do) or every pair
     // started after it is restarted from the corrected offset.  A speculative pair that finishes early is held in its slot
     // until its offset is confirmed.  Pairs with geometry end the streak and the chain goes back to one start at a time.
     enum { kFree = 0, kNeedEval = 1, kNeedExact = 2, kHeldDone = 3 };
-    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1; bool in_flight = false, discard = false; int seq = 0; int idle_polls = 0; };
+    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1, iters_guess = -1; bool in_flight = false, discard = false; int seq = 0; int idle_polls = 0; };
     HostSlot slots[kGeoSlots];
     int next_admit = 0, done_pairs = 0;
     for (int q = 0; q < kGeoSlots; ++q) G.h_decide.p[q].seq = 0;
@@ -320,6 +325,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     long long chain_offset = offset;  // offset of the next pair when the chain is empty
     int noise_streak = 0;           // pairs in a row that consumed the whole budget
     constexpr int kSpecDepth = 3;
+    constexpr int kGuessDepth = 2;    // pairs started on a predecessor's LIKELY count (first trigger candidate, exact roots pending)
     constexpr int kFirstRange = 192;  // iterations of a pair's first range while pairs with geometry are about
     auto start_pair = [&](int sl, int pair, long long off) -> int {
       AcState S0;
@@ -343,18 +349,21 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       HostSlot& H = slots[sl];
       // (a restart while the slot's previous launches are still running: they come first in its stream; their verdict is dropped)
       if (H.in_flight) H.discard = true;
-      H.state = kNeedEval; H.pair = pair; H.lo = R0.lo; H.hi = R0.hi; H.offset = off; H.iters_final = -1;
+      H.state = kNeedEval; H.pair = pair; H.lo = R0.lo; H.hi = R0.hi; H.offset = off; H.iters_final = -1; H.iters_guess = -1;
       return MVGCUDA_OK;
     };
     while (done_pairs < nb) {
       // admissions
       while (next_admit < nb) {
         const int depth = noise_streak >= 2 ? kSpecDepth : 0;
-        if ((int)chain.size() > depth) break;
+        // (the youngest pair waits for the exact roots of its first trigger candidate: its likely count is known already)
+        const bool on_guess = !chain.empty() && (int)chain.size() <= kGuessDepth && slots[chain.back()].iters_guess >= 0;
+        if ((int)chain.size() > depth && !on_guess) break;
         int sl = -1;
-        for (int q = 0; q < kGeoSlots; ++q) if (slots[q].state == kFree) { sl = q; break; }
+        for (int q = 0; q < n_slots; ++q) if (slots[q].state == kFree) { sl = q; break; }
         if (sl < 0) break;
-        const long long off = chain.empty() ? chain_offset : slots[chain.back()].offset + (long long)sample * iterations;
+        const int assumed = chain.empty() ? 0 : (slots[chain.back()].iters_guess >= 0 ? slots[chain.back()].iters_guess : iterations);
+        const long long off = chain.empty() ? chain_offset : slots[chain.back()].offset + (long long)sample * assumed;
         rc = start_pair(sl, next_admit, off);
         if (rc) return rc;
         chain.push_back(sl);
@@ -417,6 +426,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
           if (H.discard) { H.discard = false; continue; }   // the verdict of a refuted start
           const DecideOut D = *const_cast<const DecideOut*>(G.h_decide.p + q);
           if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
+          if (D.status == 1 && D.iters_guess >= 0) H.iters_guess = D.iters_guess;
           if (D.status == 1) {
             H.state = kNeedExact; H.it = D.it;
             for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
