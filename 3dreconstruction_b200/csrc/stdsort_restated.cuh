@@ -27,6 +27,10 @@
 namespace mvgcuda {
 namespace geo {
 
+#if defined(MVG_SORT_STATS) && !defined(__CUDA_ARCH__)
+static long g_ss_heap_sorts = 0;
+#endif
+
 struct SortArr {
   double* e;
   int* i;
@@ -151,7 +155,13 @@ MVG_GEO_HD int libstdcxx_sort(double* e, int* idx, int n) {
     --sp;
     int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
     while (last - first > 16) {
-      if (depth == 0) { ss_heap_sort(A, first, last); break; }
+      if (depth == 0) {
+#if defined(MVG_SORT_STATS) && !defined(__CUDA_ARCH__)
+        ++g_ss_heap_sorts;  // (tests: how often the depth limit was reached)
+#endif
+        ss_heap_sort(A, first, last);
+        break;
+      }
       --depth;
       const int mid = first + (last - first) / 2;
       ss_move_median_to_first(A, first, first + 1, mid, last - 1);

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <utility>
 #include "../../3dreconstruction_b200/csrc/acransac_core.cuh"
+#define MVG_SORT_STATS 1
 #include "../../3dreconstruction_b200/csrc/stdsort_restated.cuh"
 
 extern "C" {
@@ -170,7 +171,33 @@ int main() {
       for (int i = 0; i < n && same; ++i) same = (int)buf[64 + i].second == gi[i];
       if (!same) { ++differ; std::printf("std::sort restatement differs on structured case %d\n", t); }
     }
-    std::printf("std::sort restated: %ld arrays (%ld with NaNs), %ld differ, %ld left the array (not compared)\n", cases, with_nan, differ, left);
+    // median-of-3 killer sequences (Musser 1997): every partition peels off two elements, the depth limit 2 floor(log2 n)
+    // is reached and the rest of the range goes through the heap-sort branch -- with and without NaNs sprinkled in
+    for (int t = 0; t < 24; ++t) {
+      const int n = 2 * (300 + 211 * t), k = n / 2;
+      std::vector<double> e(n);
+      for (int i = 1; i <= k; ++i) {
+        if (i & 1) { e[i - 1] = i; e[i] = k + i; }
+        e[k + i - 1] = 2 * i;
+      }
+      if (t % 3 == 1) for (int i = 5; i < n; i += 97) e[i] = std::nan("");
+      if (t % 3 == 2) for (int i = 0; i < n; i += 3) e[i] = std::nan("");
+      std::vector<EI> buf(n + 128);
+      for (int i = 0; i < 64; ++i) { buf[i] = EI(-INFINITY, 0); buf[64 + n + i] = EI(INFINITY, (size_t)-1); }
+      for (int i = 0; i < n; ++i) buf[64 + i] = EI(e[i], (size_t)i);
+      std::sort(buf.begin() + 64, buf.begin() + 64 + n);
+      std::vector<int> gi(n);
+      for (int i = 0; i < n; ++i) gi[i] = i;
+      const int la = libstdcxx_sort(e.data(), gi.data(), n);
+      ++cases;
+      if (la) { ++left; continue; }
+      bool same = true;
+      for (int i = 0; i < n && same; ++i) same = (int)buf[64 + i].second == gi[i];
+      if (!same) { ++differ; std::printf("std::sort restatement differs on killer sequence %d\n", t); }
+    }
+    std::printf("std::sort restated: %ld arrays (%ld with NaNs), %ld differ, %ld left the array (not compared), heap-sort branch taken %ld times\n",
+                cases, with_nan, differ, left, mvgcuda::geo::g_ss_heap_sorts);
+    if (mvgcuda::geo::g_ss_heap_sorts == 0) { std::printf("the depth-limit branch was never exercised\n"); ++bad; }
     if (differ) ++bad;
   }
   std::printf(bad ? "ACRANSAC CORE FAILED\n" : "ACRANSAC CORE OK\n");
