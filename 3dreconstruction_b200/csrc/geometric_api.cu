@@ -18,6 +18,7 @@
 #include "../../include/mvgcuda.h"
 #include "acransac_kernels.cuh"
 #include "host_util.cuh"
+#include "pair_chain.h"
 
 using namespace mvgcuda;
 using namespace mvgcuda::geo;
@@ -306,26 +307,13 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
     // evaluation of its pending range (or the re-evaluation of one iteration with roots from THIS machine's C library),
     // its accounting warp, the copy of the verdict, an event the host polls.  No pair waits for another one's kernels.
     //
-    // Speculative starts: (1) a pair whose first trigger candidate waits for its exact roots will, if the candidate is
-    // confirmed (it almost always is), run candidate + 1 + reserve iterations: its successor starts on that guess, one
-    // round early.  (2) A pair that finds no meaningful model runs exactly `iterations` iterations, and in a large
-    // exhaustive collection most pairs are of that kind.  After two such pairs in a row up to kSpecDepth FURTHER pairs are
-    // started at the offsets that assumption gives (each is an upper bound, so the stream window covers them); when a
-    // pair's count becomes final the next one is either confirmed (its offset was right: nothing to do) or every pair
-    // started after it is restarted from the corrected offset.  A speculative pair that finishes early is held in its slot
-    // until its offset is confirmed.  Pairs with geometry end the streak and the chain goes back to one start at a time.
-    enum { kFree = 0, kNeedEval = 1, kNeedExact = 2, kHeldDone = 3 };
-    struct HostSlot { int state = kFree; int pair = -1; int lo = 0, hi = 0; int it = 0; double P[4]; long long offset = 0; int iters_final = -1, iters_guess = -1; bool in_flight = false, discard = false; int seq = 0; int idle_polls = 0; };
+    // The order of the starts, the offsets they assume and what happens when an assumption fails: pair_chain.h.
+    enum { kNeedEval = 1, kNeedExact = 2 };
+    struct HostSlot { int need = kNeedEval; int lo = 0, hi = 0; int it = 0; double P[4]; bool in_flight = false, discard = false; int seq = 0; int idle_polls = 0; };
     HostSlot slots[kGeoSlots];
-    int next_admit = 0, done_pairs = 0;
     for (int q = 0; q < kGeoSlots; ++q) G.h_decide.p[q].seq = 0;
     int launch_seq = 0;
-    std::deque<int> chain;          // slots of the pairs in flight whose iteration count is still open, oldest first; only
-                                    // the front one has a definite offset, the others were started speculatively
-    long long chain_offset = offset;  // offset of the next pair when the chain is empty
-    int noise_streak = 0;           // pairs in a row that consumed the whole budget
-    constexpr int kSpecDepth = 3;
-    constexpr int kGuessDepth = 2;    // pairs started on a predecessor's LIKELY count (first trigger candidate, exact roots pending)
+    PairChain chain(n_slots, nb, sample, iterations, offset);
     constexpr int kFirstRange = 192;  // iterations of a pair's first range while pairs with geometry are about
     auto start_pair = [&](int sl, int pair, long long off) -> int {
       AcState S0;
@@ -334,7 +322,7 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       R0.pair = pair; R0.lo = S0.iter; R0.hi = ac_range_end(S0); R0.n_index = S0.n_index; R0.offset = off;
       // pairs with geometry about: only the head of the first phase at first -- their trigger is almost always in it, and
       // everything evaluated after a trigger is thrown away (a no-model pair pays one more round for the rest)
-      if (noise_streak < 2 && R0.hi > kFirstRange) R0.hi = kFirstRange;
+      if (chain.geometry_about() && R0.hi > kFirstRange) R0.hi = kFirstRange;
       G.h_state.p[sl] = S0;
       G.h_round.p[sl] = R0;
       GEO_CHECK(ctx, cudaStreamWaitEvent(G.slot_stream[sl], G.ev_prep, 0));  // the batch's points are normalised
@@ -349,25 +337,18 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       HostSlot& H = slots[sl];
       // (a restart while the slot's previous launches are still running: they come first in its stream; their verdict is dropped)
       if (H.in_flight) H.discard = true;
-      H.state = kNeedEval; H.pair = pair; H.lo = R0.lo; H.hi = R0.hi; H.offset = off; H.iters_final = -1; H.iters_guess = -1;
+      H.need = kNeedEval; H.lo = R0.lo; H.hi = R0.hi;
       return MVGCUDA_OK;
     };
-    while (done_pairs < nb) {
+    while (!chain.finished()) {
       // admissions
-      while (next_admit < nb) {
-        const int depth = noise_streak >= 2 ? kSpecDepth : 0;
-        // (the youngest pair waits for the exact roots of its first trigger candidate: its likely count is known already)
-        const bool on_guess = !chain.empty() && (int)chain.size() <= kGuessDepth && slots[chain.back()].iters_guess >= 0;
-        if ((int)chain.size() > depth && !on_guess) break;
-        int sl = -1;
-        for (int q = 0; q < n_slots; ++q) if (slots[q].state == kFree) { sl = q; break; }
-        if (sl < 0) break;
-        const int assumed = chain.empty() ? 0 : (slots[chain.back()].iters_guess >= 0 ? slots[chain.back()].iters_guess : iterations);
-        const long long off = chain.empty() ? chain_offset : slots[chain.back()].offset + (long long)sample * assumed;
-        rc = start_pair(sl, next_admit, off);
-        if (rc) return rc;
-        chain.push_back(sl);
-        ++next_admit;
+      {
+        int sl, pair;
+        long long off;
+        while (chain.admit(&sl, &pair, &off)) {
+          rc = start_pair(sl, pair, off);
+          if (rc) return rc;
+        }
       }
       // launches: every slot with something to do and nothing in flight gets, on ITS stream, the evaluation of its
       // pending range followed by its accounting warp -- or, in one launch, the re-evaluation of one iteration with roots
@@ -375,10 +356,10 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
       // straight into page-locked host memory, sequence number last; the host polls that number: no copy, no event
       for (int q = 0; q < kGeoSlots; ++q) {
         HostSlot& H = slots[q];
-        if (H.in_flight || (H.state != kNeedEval && H.state != kNeedExact)) continue;
+        if (H.in_flight || chain.slot(q).state != PairChain::kActive) continue;
         cudaStream_t sq = G.slot_stream[q];
         H.seq = ++launch_seq;
-        if (H.state == kNeedEval) {
+        if (H.need == kNeedEval) {
           EvalList EL;
           EL.n = 1; EL.slot[0] = q; EL.first_warp[0] = 0;
           // a narrow range is bound by the latency of one warp (the SVD chain, then its evaluations one after the other):
@@ -425,21 +406,14 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
           ++completed;
           if (H.discard) { H.discard = false; continue; }   // the verdict of a refuted start
           const DecideOut D = *const_cast<const DecideOut*>(G.h_decide.p + q);
-          if (H.iters_final < 0 && D.iters_final >= 0) H.iters_final = D.iters_final;
-          if (D.status == 1 && D.iters_guess >= 0) H.iters_guess = D.iters_guess;
+          chain.note_counts(q, D.iters_final, D.status == 1 ? D.iters_guess : -1);
           if (D.status == 1) {
-            H.state = kNeedExact; H.it = D.it;
+            H.need = kNeedExact; H.it = D.it;
             for (int c = 0; c < 4; ++c) H.P[c] = D.P[c];
           } else if (D.status == 2) {
-            const bool speculative = std::find(chain.begin(), chain.end(), q) != chain.end() && chain.front() != q;
-            if (speculative) {
-              H.state = kHeldDone;     // its offset is not confirmed yet
-            } else {
-              H.state = kFree;
-              ++done_pairs;
-            }
+            chain.pair_done(q);      // counted now, or held until its offset is confirmed
           } else {
-            H.state = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
+            H.need = kNeedEval; H.lo = D.next.lo; H.hi = D.next.hi;
           }
         }
         if (!any_in_flight) return fail(ctx, "geometric_filter: internal error (no pair in flight)");
@@ -454,33 +428,16 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
           }
         }
       }
-      // the chain: a front pair whose count is final leaves it and confirms or refutes the offset of the next one
-      while (!chain.empty() && slots[chain.front()].iters_final >= 0) {
-        const HostSlot& F = slots[chain.front()];
-        const long long next_off = F.offset + (long long)sample * F.iters_final;
-        noise_streak = F.iters_final == iterations ? noise_streak + 1 : 0;
-        chain.pop_front();
-        if (chain.empty()) { chain_offset = next_off; break; }
-        if (slots[chain.front()].offset == next_off) {
-          HostSlot& N = slots[chain.front()];
-          if (N.state == kHeldDone) { N.state = kFree; ++done_pairs; }   // (its count is final too: it leaves on the next turn)
-          continue;
-        }
-        long long off = next_off;   // refuted: everything started after it starts again
-        for (size_t c = 0; c < chain.size(); ++c) {
-          rc = start_pair(chain[c], slots[chain[c]].pair, off);
-          if (rc) return rc;
-          off += (long long)sample * iterations;
-        }
-        ++respeculated;
-        break;
-      }
+      // the chain: front pairs whose count is final leave it and confirm or refute the offset of the next one
+      rc = chain.resolve(start_pair);
+      if (rc) return rc;
     }
+    respeculated += chain.refuted();
     for (int q = 0; q < kGeoSlots; ++q) GEO_CHECK(ctx, cudaStreamSynchronize(G.slot_stream[q]));  // (idle by now: the verdicts are in)
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_count.p, G.d_out_count.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaMemcpyAsync(G.h_out_iters.p, G.d_out_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     GEO_CHECK(ctx, cudaStreamSynchronize(st));
-    const long long offset_after = chain_offset;
+    const long long offset_after = chain.next_offset();
     // values generated beyond what the batch consumed belong to the next batch (or stay unused after the last one)
     window.assign(G.h_stream.p + (offset_after - batch_base), G.h_stream.p + (gen_pos - batch_base));
     win_base = offset_after;

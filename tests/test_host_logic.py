@@ -154,3 +154,13 @@ def test_upload_friendly_order_is_a_permutation_with_a_streamable_head():
     got = pkg.upload_friendly_order(shard, head_images=20)
     assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, shard.tolist()))
     assert len(pkg.upload_friendly_order(np.zeros((0, 2), np.int32))) == 0
+
+
+def test_pair_chain_model(tmp_path):
+    """csrc/pair_chain.h (when the geometric filter starts its pairs and at which rand() offset: speculative starts, guesses,
+    refutations, held pairs) under a randomised model of the pipeline -- 4,000 collections, verdicts in random order, wrong
+    starts reporting arbitrary counts: every pair is counted once and its last start is at the reference's offset."""
+    exe = str(tmp_path / "test_pair_chain")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "native", "test_pair_chain.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PAIR CHAIN OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
