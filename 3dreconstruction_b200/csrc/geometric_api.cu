@@ -217,12 +217,16 @@ extern "C" int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double pre
   float gpu_ms = 0.f;
   int launches = 0;
 
+  // (tests: MVGCUDA_GEO_BATCH_PAIRS cuts a small collection into several batches -- offsets and generated-but-unconsumed
+  // rand() values carry over from one to the next)
+  int batch_pairs = kGeoBatchPairs;
+  if (const char* v = getenv("MVGCUDA_GEO_BATCH_PAIRS")) batch_pairs = std::max(1, std::min(kGeoBatchPairs, atoi(v)));
   std::vector<std::vector<int32_t> > kept(active.size());  // filtered matches of the active pairs
   size_t a0 = 0;
   while (a0 < active.size()) {
     size_t a1 = a0;
     long long tot = 0;
-    while (a1 < active.size() && (a1 - a0) < (size_t)kGeoBatchPairs) {
+    while (a1 < active.size() && (a1 - a0) < (size_t)batch_pairs) {
       const long long c = counts[active[a1]];
       if (a1 > a0 && tot + c > kGeoBatchMatches) break;
       tot += c;
