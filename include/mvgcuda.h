@@ -226,7 +226,8 @@ int mvgcuda_export_matches(mvgcuda_ctx* ctx, const int32_t* pairs, const char* p
  * Scheduling (pairs in flight on their own streams, pairs started ahead on the assumption that their predecessors find no
  * model) never shows in the result: a start that turns out to be wrong is repeated from the right rand() offset.  The
  * calling thread polls page-locked memory while the GPU works.  MVGCUDA_GEO_STATS=1 in the environment prints one line of
- * counters per call to stderr (launches, re-evaluated models, refuted starts, rand() position). */
+ * counters per call to stderr (launches, re-evaluated models, refuted starts, rand() position); MVGCUDA_GEO_BATCH_PAIRS=n
+ * (tests) cuts the pair list into batches of n pairs instead of 1,024. */
 int mvgcuda_geometric_filter(mvgcuda_ctx* ctx, char model, double precision, int iterations, unsigned seed,
                              int64_t n_pairs, const int32_t* pairs, const int32_t* counts, const int64_t* offsets,
                              const int32_t* matches, const int32_t* image_sizes, mvgcuda_pair_matches* out);
