@@ -214,6 +214,11 @@ class PairMatches:
         return out
 
 
+class StagedImages:
+    """Argument tables of a streamed upload for a fixed set of host buffers (Context.stage_images)."""
+    __slots__ = ("mats", "fm", "n", "cnt", "rows", "idx", "dps", "fps")
+
+
 class Context:
     """One libmvgcuda context == one GPU."""
 
@@ -289,28 +294,39 @@ class Context:
             rws[k] = int(rows[k])
         self._check(self._lib.mvgcuda_upload_images(self._h, n, ptrs, rws, 0), "mvgcuda_upload_images")
 
-    def stream_images(self, descs: Sequence[np.ndarray], feats_xy: Optional[Sequence[np.ndarray]] = None,
-                      order: Optional[Sequence[int]] = None, wait: bool = True) -> None:
+    def stage_images(self, descs: Sequence[np.ndarray], feats_xy: Optional[Sequence[np.ndarray]] = None,
+                     order: Optional[Sequence[int]] = None) -> "StagedImages":
+        """The argument tables of a streamed upload (row counts, image order, buffer addresses), built once for a set of
+        host buffers that will be sent again and again -- e.g. page-locked staging buffers a loader refills.  The handle
+        keeps the arrays alive; their CONTENTS are read at every stream_images(staged=...) call."""
+        mats = [_as_u8_matrix(d) if len(d) else np.zeros((0, DIM), np.uint8) for d in descs]
+        n = len(mats)
+        fm = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy] if feats_xy is not None else None
+        ids = [int(k) for k in (order if order is not None else range(n))]
+        cnt = len(ids)
+        st = StagedImages()
+        st.mats, st.fm, st.n, st.cnt = mats, fm, n, cnt
+        st.rows = (C.c_int32 * max(n, 1))(*[m.shape[0] for m in mats])
+        st.idx = (C.c_int32 * max(cnt, 1))(*ids)
+        # raw addresses (cheaper than a ctypes pointer object per array: this loop is host time in front of the match call)
+        st.dps = (C.c_void_p * max(cnt, 1))(*[mats[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
+        st.fps = None
+        if fm is not None:
+            st.fps = (C.c_void_p * max(cnt, 1))(*[fm[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
+        return st
+
+    def stream_images(self, descs: Optional[Sequence[np.ndarray]] = None, feats_xy: Optional[Sequence[np.ndarray]] = None,
+                      order: Optional[Sequence[int]] = None, wait: bool = True, staged: Optional["StagedImages"] = None) -> None:
         """Same residency as upload_images (+ set_features), through the streaming entry points: one asynchronous copy per
         image on the context's upload stream, in `order` (default 0..n-1).  With wait=False the call returns while the
         copies are in flight -- a following match call starts on the pairs whose images have arrived -- and the arrays must
-        stay untouched until stream_end() (the context keeps references to them until then)."""
-        mats = [_as_u8_matrix(d) if len(d) else np.zeros((0, DIM), np.uint8) for d in descs]
-        n = len(mats)
-        rows = (C.c_int32 * max(n, 1))(*[m.shape[0] for m in mats])
-        self._check(self._lib.mvgcuda_stream_begin(self._h, n, rows), "mvgcuda_stream_begin")
-        fm = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, 2) for f in feats_xy] if feats_xy is not None else None
-        self._staged = (mats, fm)
-        ids = [int(k) for k in (order if order is not None else range(n))]
-        cnt = len(ids)
-        idx = (C.c_int32 * max(cnt, 1))(*ids)
-        # raw addresses (cheaper than a ctypes pointer object per array: this loop is host time in front of the match call)
-        dps = (C.c_void_p * max(cnt, 1))(*[mats[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
-        fps = None
-        if fm is not None:
-            fps = (C.c_void_p * max(cnt, 1))(*[fm[k].__array_interface__["data"][0] if mats[k].shape[0] else None for k in ids])
-        self._check(self._lib.mvgcuda_stream_images(self._h, cnt, idx, C.cast(dps, _u8pp), C.cast(fps, _f32pp) if fps is not None else None),
-                    "mvgcuda_stream_images")
+        stay untouched until stream_end() (the context keeps references to them until then).  `staged`: a handle from
+        stage_images() instead of the arrays (two library calls, no per-image Python work)."""
+        st = staged if staged is not None else self.stage_images(descs, feats_xy, order)
+        self._check(self._lib.mvgcuda_stream_begin(self._h, st.n, st.rows), "mvgcuda_stream_begin")
+        self._staged = st
+        self._check(self._lib.mvgcuda_stream_images(self._h, st.cnt, st.idx, C.cast(st.dps, _u8pp),
+                                                    C.cast(st.fps, _f32pp) if st.fps is not None else None), "mvgcuda_stream_images")
         if wait:
             self.stream_end()
 
@@ -554,6 +570,22 @@ class MatcherCudaAllInMemory:
         # one asynchronous copy per image (descriptors + coordinates).  wait=False: Match() starts while images still travel
         self._ctx.stream_images(d2, feats_xy, order=order, wait=wait)
         self._n = len(d2)
+        return True
+
+    def StageArrays(self, descs: Sequence[np.ndarray], feats_xy: Sequence[np.ndarray], order: Optional[Sequence[int]] = None) -> StagedImages:
+        """LoadArrays' checks and argument tables once, for buffers that are sent repeatedly (LoadStaged)."""
+        rows = [np.asarray(f).reshape(-1, 2).shape[0] for f in feats_xy]
+        d2 = []
+        for d, r in zip(descs, rows):
+            d = np.asarray(d, dtype=np.uint8).reshape(-1, DIM)
+            if d.shape[0] < r:
+                raise MvgCudaError(".feat has more rows than .desc (the reference over-reads here; refused)")
+            d2.append(d[:r])
+        return self._ctx.stage_images(d2, feats_xy, order=order)
+
+    def LoadStaged(self, staged: StagedImages, wait: bool = True) -> bool:
+        self._ctx.stream_images(staged=staged, wait=wait)
+        self._n = staged.n
         return True
 
     def LoadData(self, file_names: Sequence[str], match_dir: str) -> bool:
