@@ -400,12 +400,8 @@ def run_ours(args):
                 upload_order.append(im)
     upload_order += [k for k in range(n_images) if k not in seen]
 
-    # the argument tables (row counts, order, addresses of the pinned staging buffers) are built once; every step sends the
-    # buffers' contents again
-    staged = matcher.StageArrays(descs, feats, order=upload_order)
-
     def e2e_step():
-        matcher.LoadStaged(staged, wait=False)                             # H2D of every descriptor array + coordinates (+ norms kernel), asynchronous
+        matcher.LoadArrays(descs, feats, wait=False, order=upload_order)   # H2D of every descriptor array + coordinates (+ norms kernel), asynchronous
         pm_ = ctx.match_collection(e2e_pairs, rs, collect=False)           # kernels (rows 7-13) + D2H of the matches
         ctx.stream_end()
         return pm_
