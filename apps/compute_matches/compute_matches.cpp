@@ -235,6 +235,13 @@ int main(int argc, char** argv) {
   std::cout << " You called : \n" << argv[0] << "\n--imadir " << opt.imadir << "\n--outdir " << opt.outdir << "\n--distratio "
             << opt.dist_ratio << "\n--geometricModel " << opt.geometric_model << std::endl;
   if (!dir_exists(opt.outdir)) { std::cerr << "output directory " << opt.outdir << " does not exist" << std::endl; return EXIT_FAILURE; }
+  // the model is the first character of -g, either case; anything else ends the run (compute_matches.cpp:99-116)
+  char model_char = opt.geometric_model.empty() ? '\0' : opt.geometric_model[0];
+  if (model_char >= 'A' && model_char <= 'Z') model_char = static_cast<char>(model_char - 'A' + 'a');
+  if (model_char != 'f' && model_char != 'e' && model_char != 'h') {
+    std::cerr << "Unknown geometric model" << std::endl;
+    return EXIT_FAILURE;
+  }
 
   std::vector<std::string> names;
   std::vector<int32_t> image_sizes;
@@ -243,8 +250,8 @@ int main(int argc, char** argv) {
     return EXIT_FAILURE;
   }
   const std::string putative = opt.outdir + "/matches.putative.txt";
-  const bool filter_f = opt.geometric_model == "f" || opt.geometric_model == "h";  // the models built on the GPU
-  const char geo_model = opt.geometric_model == "h" ? 'h' : 'f';
+  const bool filter_f = model_char == 'f' || model_char == 'h';  // the models built on the GPU
+  const char geo_model = model_char == 'h' ? 'h' : 'f';
   const bool resumed = file_exists(putative);
   ImportedMatches im;
   if (resumed) {  // compute_matches.cpp:230-234

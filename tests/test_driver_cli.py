@@ -31,6 +31,20 @@ def test_usage_errors():
     assert r.returncode != 0
 
 
+def test_geometric_model_flag(tmp_path):
+    """-g takes the first character, either case; an unknown model ends the run (compute_matches.cpp:99-116).  The essential
+    model (the reference's default) is accepted but not built: the run stops after the putative stage with a message."""
+    (tmp_path / "lists.txt").write_text("a.jpg;640;480\nb.jpg;640;480\n")
+    (tmp_path / "matches.putative.txt").write_text("0 1\n0\n")
+    r = _run("-i", str(tmp_path), "-o", str(tmp_path), "-g", "x")
+    assert r.returncode != 0 and "Unknown geometric model" in r.stderr
+    for spelling in ("e", "E", "essential"):
+        r = _run("-i", str(tmp_path), "-o", str(tmp_path), "-g", spelling)
+        assert r.returncode == 0 and "only -g f and -g h" in r.stdout
+    r = _run("-i", str(tmp_path), "-o", str(tmp_path))           # default: e
+    assert r.returncode == 0 and "--geometricModel e" in r.stdout and "only -g f and -g h" in r.stdout
+
+
 def test_resume_rule_skips_matching(tmp_path):
     (tmp_path / "lists.txt").write_text("a.jpg;640;480\nb.jpg;640;480\n")
     (tmp_path / "matches.putative.txt").write_text("0 1\n0\n")
